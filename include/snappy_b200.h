@@ -1,0 +1,149 @@
+/*
+ * include/snappy_b200.h -- C ABI of libsnappy_b200.so: the B200-native (sm_100a) drop-in for
+ * Snappy.jl's compress / uncompress hot path.
+ *
+ * The reference (krm01/Snappy.jl) has no FFI of its own; its exported Julia API
+ * (src/Snappy.jl:3-5,20,38,46) is the boundary, and its own model of an FFI call for this path
+ * is test/libsnappy.jl:5-30 (ccall into the snappy-c interface).  The four host-buffer entry
+ * points below have exactly that shape so that the same ccall stubs bind to them
+ * (INTEGRATION.md shows the Julia side).  Everything is plain pointers and sizes.
+ *
+ * Stream format: varint32(uncompressed length) followed by Snappy elements; the compressed bytes
+ * are identical to what Snappy.jl's compress() produces for the same input.
+ *
+ * There is no CPU fallback: every compute entry point returns SNAPPY_B200_NO_DEVICE /
+ * SNAPPY_B200_CUDA_ERROR when no sm_100 GPU is usable.
+ */
+#ifndef SNAPPY_B200_H
+#define SNAPPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..6 map one-to-one onto the reference's error(...) sites. */
+typedef enum {
+    SNAPPY_B200_OK = 0,
+    SNAPPY_B200_INPUT_TOO_LARGE = 1,     /* src/Snappy.jl:21     "Input too large." */
+    SNAPPY_B200_INVALID_INPUT = 2,       /* src/Snappy.jl:50     "Invalid input." */
+    SNAPPY_B200_CORRUPT_COPY_OFFSET = 3, /* src/internal.jl:499  "Invalid input: corrupt copy offset" */
+    SNAPPY_B200_CORRUPT_COPY_LENGTH = 4, /* src/internal.jl:505  "Invalid input: corrupt copy length" */
+    SNAPPY_B200_CORRUPT_LITERAL = 5,     /* src/internal.jl:518  "Invalid input: corrupt literal" */
+    SNAPPY_B200_BAD_VARINT = 6,          /* src/varint.jl:36     "Could not decode varint32." */
+    SNAPPY_B200_BUFFER_TOO_SMALL = 7,    /* caller's output buffer is smaller than required */
+    SNAPPY_B200_CUDA_ERROR = 8,          /* a CUDA runtime call or kernel failed */
+    SNAPPY_B200_NO_DEVICE = 9,           /* no CUDA device / not an sm_100 part */
+    SNAPPY_B200_BAD_ARGUMENT = 10
+} snappy_b200_status;
+
+/* The reference's message for a status (exact strings of the error(...) calls above). */
+const char *snappy_b200_status_string(int status);
+/* Detail of the last failure on the calling thread (CUDA error text etc.). */
+const char *snappy_b200_last_error(void);
+
+/* Select the device (default: current device / $SNAPPY_B200_DEVICE) and create the context.
+ * Optional -- every entry point initialises lazily.  Thread-safe. */
+int snappy_b200_init(int device);
+void snappy_b200_shutdown(void);
+
+/* ---- host-buffer API: replaces test/libsnappy.jl:7,9-12 and :20-28 one for one ------------ */
+
+/* Snappy.maxlength_compressed (src/Snappy.jl:80-82): 32 + n + n/6.
+ * ccall twin: snappy_max_compressed_length (test/libsnappy.jl:7). */
+size_t snappy_b200_max_compressed_length(size_t source_length);
+
+/* Snappy.compress(::Vector{UInt8}) (src/Snappy.jl:20-36).  in/out are HOST pointers.
+ * *out_len: in = capacity of `out` (>= max_compressed_length(n)), out = compressed length.
+ * ccall twin: snappy_compress (test/libsnappy.jl:9-12). */
+int snappy_b200_compress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
+
+/* Snappy.length_uncompressed (src/Snappy.jl:90-92 -> varint.jl:12-37).  Host only, no GPU.
+ * ccall twin: snappy_uncompressed_length (test/libsnappy.jl:20-23). */
+int snappy_b200_uncompressed_length(const uint8_t *in, size_t n, size_t *result);
+
+/* Snappy.uncompress (src/Snappy.jl:46-52).  in/out are HOST pointers.
+ * *out_len: in = capacity of `out` (>= uncompressed_length), out = uncompressed length.
+ * ccall twin: snappy_uncompress (test/libsnappy.jl:25-28). */
+int snappy_b200_uncompress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
+
+/* ---- device-resident API (the GB/s targets are quoted on these) --------------------------- */
+
+/* Same as snappy_b200_compress but d_in / d_out are DEVICE pointers; `stream` is a cudaStream_t
+ * (NULL = default stream).  out_cap >= max_compressed_length(n).
+ * d_frag_index (optional, device, (nfrag+1) x uint64): side index -- byte offset inside the
+ * stream of each 64 KiB fragment's first element; entry nfrag = total stream length.
+ * nfrag = ceil(n / 65536).  The call synchronises `stream` before returning *out_len. */
+int snappy_b200_compress_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+                                size_t *out_len, uint64_t *d_frag_index, void *stream);
+
+/* Same as snappy_b200_uncompress on DEVICE pointers.  d_frag_index (optional): the side index
+ * written by snappy_b200_compress_device; NULL = arbitrary stream (segmented speculative parse).
+ * A wrong index cannot change the result: the indexed path validates every fragment and falls
+ * back to the index-free path on any inconsistency.  Synchronises `stream`. */
+int snappy_b200_uncompress_device(const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+                                  size_t *out_len, const uint64_t *d_frag_index, void *stream);
+
+/* ---- batched API: many independent streams (Parquet-page-like), one stream per page ------- */
+
+/* Page i is d_in + in_offsets[i], in_sizes[i] bytes; its stream (own varint header, own table
+ * size -- src/Snappy.jl:26-27 apply per page) is written at d_out + out_offsets[i] where the
+ * caller reserved max_compressed_length(in_sizes[i]) bytes; out_sizes[i] receives its length.
+ * All arrays are DEVICE arrays of `count` entries.  Synchronises `stream`. */
+int snappy_b200_compress_batched_device(const uint8_t *d_in, const uint64_t *d_in_offsets,
+                                        const uint32_t *d_in_sizes, size_t count, uint8_t *d_out,
+                                        const uint64_t *d_out_offsets, uint32_t *d_out_sizes,
+                                        void *stream);
+
+/* Inverse: stream i is d_in + in_offsets[i] (in_sizes[i] bytes); its bytes go to
+ * d_out + out_offsets[i], out_caps[i] = room there; out_sizes[i] receives the length and
+ * d_statuses[i] the per-page snappy_b200_status.  Returns OK when the batch ran; per-page
+ * failures are reported in d_statuses only. */
+int snappy_b200_uncompress_batched_device(const uint8_t *d_in, const uint64_t *d_in_offsets,
+                                          const uint32_t *d_in_sizes, size_t count, uint8_t *d_out,
+                                          const uint64_t *d_out_offsets, const uint32_t *d_out_caps,
+                                          uint32_t *d_out_sizes, int32_t *d_statuses, void *stream);
+
+/* ---- shard API: multi-GPU sharding on whole-fragment boundaries --------------------------- */
+
+/* Compress a contiguous run of whole 64 KiB fragments of a stream whose TOTAL length is
+ * total_len (the hash-table size comes from the total, src/Snappy.jl:27).  d_shard holds
+ * shard_len bytes starting at a multiple of 65536 inside the stream; only the last shard may
+ * be ragged.  Writes the compacted element bytes of the shard (NO varint header) to d_out and
+ * its length to *out_len; the caller concatenates the shards behind
+ * snappy_b200_encode_header(total_len).  d_frag_sizes (optional, device, one uint32 per fragment
+ * of the shard) receives each fragment's compressed size.  Synchronises `stream`. */
+int snappy_b200_compress_shard_device(const uint8_t *d_shard, size_t shard_len, uint64_t total_len,
+                                      uint8_t *d_out, size_t out_cap, size_t *out_len,
+                                      uint32_t *d_frag_sizes, void *stream);
+
+/* Decode fragments of a stream given their element byte ranges: fragment i of the shard is
+ * d_in[frag_offsets[i] .. frag_offsets[i+1]) and decodes to d_out + i*65536 (the last one may
+ * be short: out_len total bytes expected).  Used by each rank on its own slice. */
+int snappy_b200_uncompress_shard_device(const uint8_t *d_in, const uint64_t *d_frag_offsets,
+                                        size_t nfrag, uint8_t *d_out, size_t out_len, void *stream);
+
+/* varint.jl:46-69 / :12-37 on the host (the stream header). Returns bytes written (1..5). */
+int snappy_b200_encode_header(uint32_t value, uint8_t out[5]);
+int snappy_b200_parse_header(const uint8_t *in, size_t n, uint32_t *value, size_t *header_len);
+
+/* Host helper mirroring Snappy.find_match_length (src/internal.jl:344-387), which the
+ * reference's tests call directly (test/runtests.jl:172).  0-based, `limit` exclusive. */
+size_t snappy_b200_find_match_length(const uint8_t *a, size_t i1, size_t i2, size_t limit);
+
+/* ---- instrumentation (bench.py roofline) ------------------------------------------------- */
+
+/* Device time, in milliseconds, of the dominant kernel of the last compress (which=0) or
+ * uncompress (which=1) call on this thread's context, measured with CUDA events recorded on
+ * the launching stream around that kernel; and the number of kernels that call launched. */
+float snappy_b200_last_kernel_ms(int which);
+int snappy_b200_last_launch_count(int which);
+/* Selects kernel variants for A/B testing (0 = default).  See DESIGN.md. */
+void snappy_b200_set_option(const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

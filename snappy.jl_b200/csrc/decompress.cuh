@@ -1,0 +1,296 @@
+// decompress.cuh -- Snappy raw-format decoder kernels for sm_100a, following the reference's
+// decoder semantics (src/Snappy.jl:46-52, src/internal.jl:411-527) including its quirks
+// (strict `ip < last` loop bound, zero-padded trailer, UInt32 literal-length wrap-around).
+#pragma once
+#include "common.cuh"
+
+namespace sb200 {
+
+struct DecodeResult {
+    int status;        // ST_* of the first failing element in stream order (ST_OK if none)
+    u32 fallback;      // indexed path: some fragment was inconsistent with the side index
+    u64 produced;      // output bytes produced
+    u64 err_op;        // output position at which the error fired
+};
+
+// One element header decoded from its tag byte `c` and the (zero-padded) 4 bytes behind it.
+// CHAR_TABLE (src/internal.jl:47-80) is evaluated arithmetically: bits 0-7 length,
+// 8-10 offset high bits, 11-13 extra bytes; WORDMASK (:83-85) becomes a shift.
+struct Element {
+    u32 len;      // literal: byte count (mod 2^32); copy: 1..64
+    u32 offset;   // copy offset (0 for literals)
+    u32 extra;    // bytes after the tag that belong to the header
+    bool is_copy;
+};
+
+__device__ __forceinline__ Element decode_tag(u32 c, u32 tag4) {
+    Element e;
+    const u32 kind = c & 3, hi = c >> 2;
+    if (kind == 0) {
+        e.is_copy = false;
+        e.offset = 0;
+        if (hi < 60) {
+            e.extra = 0;
+            e.len = hi + 1;
+        } else {
+            e.extra = hi - 59;
+            u32 mask = (e.extra == 4) ? 0xffffffffu : ((1u << (8 * e.extra)) - 1);
+            e.len = 1 + (tag4 & mask);  // src/internal.jl:462, UInt32 arithmetic wraps
+        }
+    } else if (kind == 1) {
+        e.is_copy = true;
+        e.extra = 1;
+        e.len = 4 + (hi & 7);
+        e.offset = ((c >> 5) << 8) + (tag4 & 0xff);
+    } else if (kind == 2) {
+        e.is_copy = true;
+        e.extra = 2;
+        e.len = hi + 1;
+        e.offset = tag4 & 0xffff;
+    } else {
+        e.is_copy = true;
+        e.extra = 4;
+        e.len = hi + 1;
+        e.offset = tag4;
+    }
+    return e;
+}
+
+// tag byte at ip and the next 4 bytes, zero-padded past `end` (src/internal.jl:426-430)
+__device__ __forceinline__ void load_tag(const u8* __restrict__ in, u64 ip, u64 end, u32& c,
+                                         u32& tag4) {
+    if (ip + 12 <= end) {
+        // three aligned 32-bit words cover the 5 bytes at any misalignment of the address
+        const uintptr_t pa = reinterpret_cast<uintptr_t>(in + ip);
+        const u32* w = reinterpret_cast<const u32*>(pa & ~(uintptr_t)3);
+        const u32 sh = (u32)(pa & 3) * 8;
+        u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        u32 lo = __funnelshift_r(w0, w1, sh);
+        u32 hi = __funnelshift_r(w1, w2, sh);
+        c = lo & 0xff;
+        tag4 = __funnelshift_r(lo, hi, 8);
+    } else {
+        c = in[ip];
+        tag4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (ip + 1 + k < end) tag4 |= (u32)in[ip + 1 + k] << (8 * k);
+    }
+}
+
+// warp-cooperative copies -----------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_literal(u8* __restrict__ dst, const u8* __restrict__ src,
+                                                  u64 len, u32 lane) {
+    // 16-byte vector body when the misalignments agree, bytes otherwise
+    if (len >= 64 && ((reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        u64 head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+        for (u64 i = lane; i < head; i += 32) dst[i] = src[i];
+        u64 nvec = (len - head) >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+        for (u64 j = lane; j < nvec; j += 32) d4[j] = __ldg(s4 + j);
+        for (u64 i = head + (nvec << 4) + lane; i < len; i += 32) dst[i] = src[i];
+    } else {
+        for (u64 i = lane; i < len; i += 32) dst[i] = src[i];
+    }
+}
+
+// out[op+i] = out[op-offset+i], ascending i (src/internal.jl:477-481): for offset < len the
+// source pattern of `offset` bytes repeats, so byte i reads op - offset + (i mod offset).
+__device__ __forceinline__ void warp_copy_backref(u8* out, u64 op, u32 offset, u32 len, u32 lane) {
+    const u8* src = out + (op - offset);
+    u8* dst = out + op;
+    if (offset >= len) {
+        for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
+    } else {
+        for (u32 i = lane; i < len; i += 32) dst[i] = src[i % offset];
+    }
+}
+
+// Exact serial decoder: one warp walks a stream element by element, reproducing the
+// reference's status for every input (first error in stream order).  Used for arbitrary streams
+// until the speculative parse has produced an index, and as the arbiter whenever the fast paths
+// see anything inconsistent.  `ip0` is the first byte after the varint header.
+__device__ __forceinline__ int decode_exact_warp(const u8* __restrict__ in, u64 L, u64 ip0,
+                                                 u8* __restrict__ out, u64 n, u32 lane,
+                                                 u64& produced) {
+    u64 ip = ip0, op = 0;
+    int status = ST_OK;
+    while (ip + 1 < L) {  // src/internal.jl:416
+        u32 c, tag4;
+        load_tag(in, ip, L, c, tag4);
+        ip += 1;
+        Element e = decode_tag(c, tag4);
+        ip += e.extra;
+        if (e.is_copy) {
+            if (e.offset == 0 || (u64)e.offset > op) { status = ST_CORRUPT_COPY_OFFSET; break; }  // :499
+            if (n - op < e.len) { status = ST_CORRUPT_COPY_LENGTH; break; }                       // :505
+            warp_copy_backref(out, op, e.offset, e.len, lane);
+            op += e.len;
+        } else {
+            // avail_in may be negative when the header bytes ran past the end (:517-518)
+            long long avail_in = (long long)L - (long long)ip;
+            if (n - op < (u64)e.len || avail_in < (long long)e.len) { status = ST_CORRUPT_LITERAL; break; }
+            warp_copy_literal(out + op, in + ip, e.len, lane);
+            op += e.len;
+            ip += e.len;
+        }
+        __syncwarp();
+    }
+    if (status == ST_OK && op != n) status = ST_INVALID_INPUT;  // src/Snappy.jl:50
+    produced = op;
+    return status;
+}
+
+__global__ void __launch_bounds__(32)
+k_decode_serial(const u8* __restrict__ in, u64 L, u64 ip0, u8* __restrict__ out, u64 n,
+                DecodeResult* __restrict__ res) {
+    const u32 lane = lane_id();
+    u64 produced;
+    int status = decode_exact_warp(in, L, ip0, out, n, lane, produced);
+    if (lane == 0) {
+        res->status = status;
+        res->produced = produced;
+        res->err_op = produced;
+    }
+}
+
+// Indexed decoder: one warp per 64 KiB output fragment, whose elements are
+// in[frag_off[f] .. frag_off[f+1]) (side index from the compressor, or from the parse kernels).
+// Elements are parsed 32 at a time (warp-uniform walk; lane k keeps element k), then executed
+// lane-per-element in dependency rounds: an element may run once every output byte it reads lies
+// below the `frontier` (the destination of the first unfinished element of the batch).
+// Anything that is not a clean, self-contained fragment sets res->fallback and the caller reruns
+// the exact serial decoder, so a wrong index can never change the result.
+constexpr u32 kDecodeWarpsPerCta = 4;
+constexpr u32 kLongLiteral = 32;  // literals longer than this are copied by the whole warp
+
+// Decode the self-contained element run in[ip .. ie) into o[0 .. on).  Returns false when the run
+// is not clean (bad element, reaches before o, does not end exactly at ie / on).
+__device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 ip, const u64 ie,
+                                                 u8* __restrict__ o, const u32 on, const u32 lane) {
+    u32 op = 0;
+    while (ip < ie) {
+        // ---- parse up to 32 elements
+        u32 cnt = 0;
+        u32 my_len = 0, my_dst = 0, my_off = 0;
+        u64 my_src = 0;
+        bool my_copy = false;
+        while (cnt < 32 && ip < ie) {
+            u32 c, tag4;
+            load_tag(in, ip, ie, c, tag4);
+            Element e = decode_tag(c, tag4);
+            ip += 1 + e.extra;
+            if (e.is_copy) {
+                if (ip > ie || e.offset == 0 || e.offset > op || e.len > on - op) return false;
+                if (cnt == lane) { my_len = e.len; my_dst = op; my_off = e.offset; my_copy = true; }
+                cnt++;
+            } else {
+                if (ip > ie || (u64)e.len > ie - ip || e.len > on - op) return false;
+                if (e.len > kLongLiteral) {
+                    warp_copy_literal(o + op, in + ip, e.len, lane);
+                } else {
+                    if (cnt == lane) { my_len = e.len; my_dst = op; my_src = ip; my_copy = false; }
+                    cnt++;
+                }
+                ip += e.len;
+            }
+            op += e.len;
+        }
+        // ---- execute the batch in dependency rounds
+        const u32 active = (cnt == 32) ? kFullMask : ((1u << cnt) - 1);
+        const bool mine = lane < cnt;
+        // highest output byte (exclusive) this element reads; literals read none
+        const u32 need = (mine && my_copy) ? min(my_dst - my_off + my_len, my_dst) : 0;
+        u32 done = ~active;
+        __syncwarp();  // long literals written above are visible to the copies below
+        while (done != kFullMask) {
+            const u32 first = (u32)__ffs((int)~done) - 1;
+            const u32 frontier = __shfl_sync(kFullMask, my_dst, first);
+            const bool ready = mine && !((done >> lane) & 1) && (need <= frontier);
+            if (ready) {
+                u8* d = o + my_dst;
+                if (my_copy) {
+                    const u8* s = o + (my_dst - my_off);
+                    if (my_off >= my_len) {
+                        for (u32 i = 0; i < my_len; i++) d[i] = s[i];
+                    } else {
+                        for (u32 i = 0; i < my_len; i++) d[i] = s[i % my_off];
+                    }
+                } else {
+                    const u8* s = in + my_src;
+                    for (u32 i = 0; i < my_len; i++) d[i] = __ldg(s + i);
+                }
+            }
+            __syncwarp();
+            done |= __ballot_sync(kFullMask, ready);
+        }
+    }
+    return ip == ie && op == on;
+}
+
+// in_begin / in_end: the element bytes of the whole stream are in[in_begin .. in_end); the index
+// must start at in_begin and end at in_end.
+__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32)
+k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag,
+                   u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
+                   DecodeResult* __restrict__ res) {
+    const u32 lane = lane_id();
+    const u32 f = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
+    if (f >= nfrag) return;
+    const u64 ip = frag_off[f];
+    const u64 ie = frag_off[f + 1];
+    const u64 ob = (u64)f * kBlockSize;
+    const u32 on = (u32)((out_len - ob < kBlockSize) ? (out_len - ob) : kBlockSize);
+    bool ok = (ie >= ip) && (ie <= in_end) && (f != 0 || ip == in_begin) &&
+              (f != nfrag - 1 || ie == in_end);
+    if (ok) ok = decode_fast_warp(in, ip, ie, out + ob, on, lane);
+    if (!ok && lane == 0) atomicOr(&res->fallback, 1u);
+}
+
+// Batched pages: one warp per independent stream (own varint header).  Fast path first; the exact
+// decoder arbitrates anything unusual so the per-page status equals the reference's.
+__device__ __forceinline__ int parse_varint_dev(const u8* __restrict__ in, u64 L, u32& value, u32& hdr) {
+    u32 result = 0;
+    for (u32 i = 0; i < 5; i++) {  // src/varint.jl:12-37
+        if (i >= L) return ST_BAD_VARINT;
+        u32 b = in[i];
+        result |= (b & 0x7f) << (7 * i);
+        if (i < 4 ? (b < 0x80) : (b < 0x10)) {
+            value = result;
+            hdr = i + 1;
+            return ST_OK;
+        }
+    }
+    return ST_BAD_VARINT;
+}
+
+__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32)
+k_decode_pages(const u8* __restrict__ in, const u64* __restrict__ in_off,
+               const u32* __restrict__ in_size, u32 count, u8* __restrict__ out,
+               const u64* __restrict__ out_off, const u32* __restrict__ out_cap,
+               u32* __restrict__ out_size, int* __restrict__ statuses) {
+    const u32 lane = lane_id();
+    const u32 pg = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
+    if (pg >= count) return;
+    const u8* pin = in + in_off[pg];
+    const u64 L = in_size[pg];
+    u8* pout = out + out_off[pg];
+    u32 claimed = 0, hdr = 0;
+    int status = parse_varint_dev(pin, L, claimed, hdr);
+    if (status == ST_OK && claimed > out_cap[pg]) status = 7;  // SNAPPY_B200_BUFFER_TOO_SMALL
+    if (status == ST_OK) {
+        bool ok = (claimed <= kBlockSize) && decode_fast_warp(pin, hdr, L, pout, claimed, lane);
+        if (!ok) {
+            u64 produced;
+            __syncwarp();
+            status = decode_exact_warp(pin, L, hdr, pout, claimed, lane, produced);
+        }
+    }
+    if (lane == 0) {
+        statuses[pg] = status;
+        out_size[pg] = (status == ST_OK) ? claimed : 0;
+    }
+}
+
+}  // namespace sb200

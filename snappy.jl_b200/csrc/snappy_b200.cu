@@ -1,0 +1,659 @@
+// snappy_b200.cu -- C ABI (include/snappy_b200.h) + device buffer manager for libsnappy_b200.so.
+//
+// Host side of the drop-in boundary: what src/Snappy.jl:20-52 does around the codec kernels
+// (length check, varint header, buffer sizing, final length, error mapping) lives here in C++;
+// the codec itself runs only as sm_100a kernels (compress.cuh / decompress.cuh).  No CPU fallback.
+#include "../../include/snappy_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "compress.cuh"
+#include "decompress.cuh"
+#include "parse.cuh"
+
+using namespace sb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only device allocation
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Options {
+    int compress_variant = 0;   // 0 = default
+    int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
+    int timing = 1;             // record CUDA events around the dominant kernel
+};
+
+struct Context {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    // scratch for compress
+    DevBuf scratch, frag_sizes, frag_offsets;
+    // scratch for decode
+    DevBuf result, parse_a, parse_b, parse_c, index;
+    // staging for the host-buffer API
+    DevBuf stage_in, stage_out;
+    void* pinned = nullptr;  // small pinned readback area (4 KiB)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[2] = {0.f, 0.f};
+    int last_launches[2] = {0, 0};
+    bool ev_pending[2] = {false, false};
+    Options opt;
+};
+
+Context g_ctx;
+
+int fail_cuda(cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    g_last_error = buf;
+    return SNAPPY_B200_CUDA_ERROR;
+}
+
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+int ctx_init_locked(int device) {
+    Context& c = g_ctx;
+    if (c.ready) return SNAPPY_B200_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return SNAPPY_B200_NO_DEVICE;
+    }
+    if (device < 0) {
+        const char* env = getenv("SNAPPY_B200_DEVICE");
+        if (env) {
+            device = atoi(env);
+        } else if (cudaGetDevice(&device) != cudaSuccess) {
+            device = 0;
+        }
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; libsnappy_b200 holds sm_100a code only", device,
+                 prop.major, prop.minor);
+        g_last_error = buf;
+        return SNAPPY_B200_NO_DEVICE;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    CU(cudaFuncSetAttribute(k_compress_fragments_serial, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompressSmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_pages, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompressSmemBytes));
+    CU(cudaMallocHost(&c.pinned, 4096));
+    for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
+    CU(c.result.ensure(sizeof(DecodeResult)));
+    c.ready = true;
+    return SNAPPY_B200_OK;
+}
+
+// collect the event pair recorded around the dominant kernel of the last call
+void harvest_timing(Context& c, int which) {
+    if (c.ev_pending[which]) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c.ev[2 * which], c.ev[2 * which + 1]) == cudaSuccess)
+            c.last_ms[which] = ms;
+        c.ev_pending[which] = false;
+    }
+}
+
+inline u32 table_shift(u64 total_len) {
+    u32 entries = 256;  // alloc_hashtable, src/internal.jl:107-113
+    while (entries < kMaxTableEntries && entries < total_len) entries <<= 1;
+    u32 lg = 0;
+    while ((1u << lg) < entries) lg++;
+    return 32 - lg;  // src/internal.jl:128
+}
+
+int encode_varint(u32 v, u8* out) {  // src/varint.jl:46-69
+    int k = 0;
+    while (v >= 0x80) {
+        out[k++] = (u8)(v | 0x80);
+        v >>= 7;
+    }
+    out[k++] = (u8)v;
+    return k;
+}
+
+int parse_varint(const u8* in, size_t n, u32* value, size_t* hdr) {  // src/varint.jl:12-37
+    u32 result = 0;
+    for (int i = 0; i < 5; i++) {
+        if ((size_t)i >= n) return SNAPPY_B200_BAD_VARINT;
+        u32 b = in[i];
+        result |= (b & 0x7f) << (7 * i);
+        if (i < 4 ? (b < 0x80) : (b < 0x10)) {
+            *value = result;
+            *hdr = (size_t)i + 1;
+            return SNAPPY_B200_OK;
+        }
+    }
+    return SNAPPY_B200_BAD_VARINT;
+}
+
+// Compress the fragments of one shard into d_out + base (elements only) and return the number of
+// bytes behind d_out (base + elements).  d_index (optional): nfrag+1 stream offsets.
+int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 total_len, u8* d_out,
+                          u64 base, u64* total_out, u64* d_index, u32* d_frag_sizes_out,
+                          cudaStream_t st) {
+    const u32 nfrag = (u32)((shard_len + kBlockSize - 1) / kBlockSize);
+    c.last_launches[0] = 0;
+    if (nfrag == 0) {
+        *total_out = base;
+        if (d_index) {
+            u64* h = (u64*)c.pinned;
+            h[0] = base;
+            CU(cudaMemcpyAsync(d_index, h, 8, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return SNAPPY_B200_OK;
+    }
+    CU(c.scratch.ensure((size_t)nfrag * kSlotStride));
+    CU(c.frag_sizes.ensure((size_t)nfrag * sizeof(u32)));
+    CU(c.frag_offsets.ensure(((size_t)nfrag + 1) * sizeof(u64)));
+    const u32 shift = table_shift(total_len);
+    u8* scratch = (u8*)c.scratch.p;
+    u32* sizes = (u32*)c.frag_sizes.p;
+    u64* offs = (u64*)c.frag_offsets.p;
+
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
+    k_compress_fragments_serial<<<nfrag, 32, kCompressSmemBytes, st>>>(d_in, (u64)shard_len, shift,
+                                                                      scratch, sizes);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[1], st));
+        c.ev_pending[0] = true;
+    }
+    k_scan_sizes<<<1, 1024, 0, st>>>(sizes, nfrag, base, offs);
+    k_compact<<<nfrag, 256, 0, st>>>(scratch, sizes, offs, d_out);
+    c.last_launches[0] = 3;
+    CU(cudaGetLastError());
+    u64* h = (u64*)c.pinned;
+    CU(cudaMemcpyAsync(h, offs + nfrag, 8, cudaMemcpyDeviceToHost, st));
+    if (d_index)
+        CU(cudaMemcpyAsync(d_index, offs, ((size_t)nfrag + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_frag_sizes_out)
+        CU(cudaMemcpyAsync(d_frag_sizes_out, sizes, (size_t)nfrag * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 0);
+    *total_out = h[0];
+    return SNAPPY_B200_OK;
+}
+
+int compress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
+                           size_t* out_len, u64* d_index, cudaStream_t st) {
+    if (n > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;  // src/Snappy.jl:21
+    if (out_cap < snappy_b200_max_compressed_length(n)) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    u8* hdr = (u8*)c.pinned + 64;
+    const int k = encode_varint((u32)n, hdr);  // src/Snappy.jl:26
+    CU(cudaMemcpyAsync(d_out, hdr, (size_t)k, cudaMemcpyHostToDevice, st));
+    u64 total = 0;
+    int rc = compress_shard_locked(c, d_in, n, n, d_out, (u64)k, &total, d_index, nullptr, st);
+    if (rc != SNAPPY_B200_OK) return rc;
+    *out_len = (size_t)total;
+    return SNAPPY_B200_OK;
+}
+
+// run the exact serial decoder over the whole stream
+int decode_exact_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
+                        cudaStream_t st) {
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    k_decode_serial<<<1, 32, 0, st>>>(d_in, (u64)n, (u64)hdr, d_out, (u64)claimed, res);
+    c.last_launches[1] += 1;
+    CU(cudaGetLastError());
+    DecodeResult* h = (DecodeResult*)((u8*)c.pinned + 128);
+    CU(cudaMemcpyAsync(h, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return h->status;
+}
+
+// decode with a device-resident index of nfrag+1 offsets; returns OK, or -1 when the fast path
+// declined (caller falls back)
+int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
+                          const u64* d_index, cudaStream_t st) {
+    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    if (nfrag == 0) return -1;
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    const u32 grid = (nfrag + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
+    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, (u64)hdr, (u64)n,
+                                                                 d_out, (u64)claimed, res);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[3], st));
+        c.ev_pending[1] = true;
+    }
+    c.last_launches[1] += 1;
+    CU(cudaGetLastError());
+    DecodeResult* h = (DecodeResult*)((u8*)c.pinned + 128);
+    CU(cudaMemcpyAsync(h, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 1);
+    return h->fallback ? -1 : SNAPPY_B200_OK;
+}
+
+// Segmented speculative parse (parse.cuh): build the side index of an arbitrary stream in
+// c.index.  Returns 0 when the index is ready, -1 when the stream is not fragment-clean or shows
+// any anomaly (the exact serial decoder then decides), or a CUDA error status (> 0).
+int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 claimed, cudaStream_t st) {
+    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    if (nfrag == 0 || n <= hdr) return -1;
+    const u64 body = n - hdr;
+    if (body / kParseChunk >= 0x7fffffffull) return -1;
+    const u32 nchunk = (u32)((body + kParseChunk - 1) / kParseChunk);
+    CU(c.parse_a.ensure((size_t)nchunk * 16));               // entry, exit
+    CU(c.parse_b.ensure((size_t)nchunk * 12 + 64));          // outb, flags, dirty, counters
+    CU(c.parse_c.ensure(((size_t)nchunk + 1) * 8));          // output offsets
+    CU(c.index.ensure(((size_t)nfrag + 1) * 8));
+    ParseArrays pa;
+    pa.entry = (u64*)c.parse_a.p;
+    pa.exit = pa.entry + nchunk;
+    pa.outb = (u32*)c.parse_b.p;
+    pa.flags = pa.outb + nchunk;
+    pa.dirty = pa.flags + nchunk;
+    pa.counters = pa.dirty + nchunk;
+    u64* out_off = (u64*)c.parse_c.p;
+    u32* h = (u32*)((u8*)c.pinned + 1024);
+
+    CU(cudaMemsetAsync(pa.dirty, 0, (size_t)nchunk * 4 + 64, st));
+    const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
+    const u32 lgrid = (nchunk + 255) / 256;
+    k_parse_chunks<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, 1);
+    c.last_launches[1] += 1;
+    bool converged = false;
+    for (int round = 0; round < 256 && !converged; round++) {
+        // several link passes per round: a long literal resolves the chunks it jumps over one
+        // pass at a time (a 64 KiB literal spans 16 chunks)
+        for (int s = 0; s < 18; s++) k_link_chunks<<<lgrid, 256, 0, st>>>((u64)n, (u64)hdr, nchunk, pa);
+        c.last_launches[1] += 18;
+        CU(cudaMemcpyAsync(h, pa.counters, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h[0] == 0) {
+            converged = true;
+        } else {
+            CU(cudaMemsetAsync(pa.counters, 0, 4, st));
+            k_parse_chunks<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, 0);
+            c.last_launches[1] += 1;
+        }
+    }
+    if (!converged) return -1;
+    k_parse_check<<<(lgrid < 1024 ? lgrid : 1024), 256, 0, st>>>((u64)n, nchunk, pa);
+    k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
+    c.last_launches[1] += 2;
+    CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + 4, out_off + nchunk, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    u64 total;
+    memcpy(&total, h + 4, 8);
+    if (h[1] != 0 || total != claimed) return -1;
+    k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off,
+                                                  (u64*)c.index.p, nfrag);
+    c.last_launches[1] += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return h[2] ? -1 : 0;
+}
+
+int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
+                             size_t* out_len, const u64* d_index, cudaStream_t st) {
+    c.last_launches[1] = 0;
+    // the varint header decides the output size (src/Snappy.jl:47)
+    u8* hb = (u8*)c.pinned + 256;
+    const size_t hn = n < 5 ? n : 5;
+    if (hn) {
+        CU(cudaMemcpyAsync(hb, d_in, hn, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    u32 claimed = 0;
+    size_t hdr = 0;
+    int rc = parse_varint(hb, hn, &claimed, &hdr);
+    if (rc != SNAPPY_B200_OK) return rc;
+    if (out_cap < claimed) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    *out_len = claimed;
+    if (c.opt.decode_variant != 1) {
+        if (d_index) {
+            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, d_index, st);
+            if (rc >= 0) return rc;
+        }
+        // arbitrary stream: segmented speculative parse builds the index on the device
+        rc = build_index_locked(c, d_in, n, hdr, claimed, st);
+        if (rc > 0) return rc;
+        if (rc == 0) {
+            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, (const u64*)c.index.p, st);
+            if (rc >= 0) return rc;
+        }
+    }
+    return decode_exact_locked(c, d_in, n, hdr, d_out, claimed, st);
+}
+
+struct Locked {
+    std::unique_lock<std::mutex> lk;
+    int rc;
+    Locked() : lk(g_ctx.mu), rc(ctx_init_locked(-1)) {
+        if (rc == SNAPPY_B200_OK) {
+            cudaError_t e = cudaSetDevice(g_ctx.device);
+            if (e != cudaSuccess) rc = fail_cuda(e, "cudaSetDevice");
+        }
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* snappy_b200_status_string(int status) {
+    switch (status) {
+        case SNAPPY_B200_OK: return "OK";
+        case SNAPPY_B200_INPUT_TOO_LARGE: return "Input too large.";
+        case SNAPPY_B200_INVALID_INPUT: return "Invalid input.";
+        case SNAPPY_B200_CORRUPT_COPY_OFFSET: return "Invalid input: corrupt copy offset";
+        case SNAPPY_B200_CORRUPT_COPY_LENGTH: return "Invalid input: corrupt copy length";
+        case SNAPPY_B200_CORRUPT_LITERAL: return "Invalid input: corrupt literal";
+        case SNAPPY_B200_BAD_VARINT: return "Could not decode varint32.";
+        case SNAPPY_B200_BUFFER_TOO_SMALL: return "output buffer too small";
+        case SNAPPY_B200_CUDA_ERROR: return "CUDA error";
+        case SNAPPY_B200_NO_DEVICE: return "no usable sm_100 CUDA device";
+        case SNAPPY_B200_BAD_ARGUMENT: return "bad argument";
+        default: return "unknown status";
+    }
+}
+
+const char* snappy_b200_last_error(void) { return g_last_error.c_str(); }
+
+int snappy_b200_init(int device) {
+    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    return ctx_init_locked(device);
+}
+
+void snappy_b200_shutdown(void) {
+    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    Context& c = g_ctx;
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    for (DevBuf* b : {&c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
+                      &c.parse_c, &c.index, &c.stage_in, &c.stage_out})
+        b->release();
+    if (c.pinned) cudaFreeHost(c.pinned);
+    c.pinned = nullptr;
+    for (auto& ev : c.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    c.ready = false;
+}
+
+size_t snappy_b200_max_compressed_length(size_t n) { return 32 + n + n / 6; }  // src/Snappy.jl:80-82
+
+int snappy_b200_encode_header(uint32_t value, uint8_t out[5]) { return encode_varint(value, out); }
+
+int snappy_b200_parse_header(const uint8_t* in, size_t n, uint32_t* value, size_t* header_len) {
+    if (!in && n) return SNAPPY_B200_BAD_ARGUMENT;
+    return parse_varint(in, n, value, header_len);
+}
+
+int snappy_b200_uncompressed_length(const uint8_t* in, size_t n, size_t* result) {
+    u32 v = 0;
+    size_t hdr = 0;
+    int rc = parse_varint(in, n, &v, &hdr);
+    if (rc == SNAPPY_B200_OK) *result = v;
+    return rc;
+}
+
+// src/internal.jl:344-387 on the host (tests call Snappy.find_match_length directly)
+size_t snappy_b200_find_match_length(const uint8_t* a, size_t i1, size_t i2, size_t limit) {
+    size_t matched = 0;
+    while (i2 + 8 <= limit) {
+        u64 x, y;
+        memcpy(&x, a + i1 + matched, 8);
+        memcpy(&y, a + i2, 8);
+        if (x != y) return matched + (size_t)(__builtin_ctzll(x ^ y) >> 3);
+        i2 += 8;
+        matched += 8;
+    }
+    while (i2 < limit && a[i1 + matched] == a[i2]) {
+        i2++;
+        matched++;
+    }
+    return matched;
+}
+
+int snappy_b200_compress_device(const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap,
+                                size_t* out_len, uint64_t* d_frag_index, void* stream) {
+    if (!out_len || (!d_in && n) || !d_out) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    return compress_device_locked(g_ctx, d_in, n, d_out, out_cap, out_len, (u64*)d_frag_index,
+                                  (cudaStream_t)stream);
+}
+
+int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap,
+                                  size_t* out_len, const uint64_t* d_frag_index, void* stream) {
+    if (!out_len || (!d_in && n)) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    return uncompress_device_locked(g_ctx, d_in, n, d_out, out_cap, out_len, (const u64*)d_frag_index,
+                                    (cudaStream_t)stream);
+}
+
+int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len) {
+    if (!out_len || (!in && n) || !out) return SNAPPY_B200_BAD_ARGUMENT;
+    if (n > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;  // src/Snappy.jl:21
+    const size_t need = snappy_b200_max_compressed_length(n);
+    if (*out_len < need) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    CU(c.stage_in.ensure(n + 16));
+    CU(c.stage_out.ensure(need + 16));
+    cudaStream_t st = 0;
+    if (n) CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
+    size_t clen = 0;
+    int rc = compress_device_locked(c, (const u8*)c.stage_in.p, n, (u8*)c.stage_out.p, need, &clen,
+                                    nullptr, st);
+    if (rc != SNAPPY_B200_OK) return rc;
+    CU(cudaMemcpyAsync(out, c.stage_out.p, clen, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_len = clen;
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len) {
+    if (!out_len || (!in && n)) return SNAPPY_B200_BAD_ARGUMENT;
+    u32 claimed = 0;
+    size_t hdr = 0;
+    int rc = parse_varint(in, n, &claimed, &hdr);  // src/Snappy.jl:47
+    if (rc != SNAPPY_B200_OK) return rc;
+    if (*out_len < claimed) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    CU(c.stage_in.ensure(n + 16));
+    CU(c.stage_out.ensure((size_t)claimed + 16));
+    cudaStream_t st = 0;
+    CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
+    size_t olen = 0;
+    rc = uncompress_device_locked(c, (const u8*)c.stage_in.p, n, (u8*)c.stage_out.p, (size_t)claimed,
+                                  &olen, nullptr, st);
+    if (rc != SNAPPY_B200_OK) return rc;
+    if (olen) CU(cudaMemcpyAsync(out, c.stage_out.p, olen, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_len = olen;
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_compress_shard_device(const uint8_t* d_shard, size_t shard_len, uint64_t total_len,
+                                      uint8_t* d_out, size_t out_cap, size_t* out_len,
+                                      uint32_t* d_frag_sizes, void* stream) {
+    if (!out_len || (!d_shard && shard_len) || !d_out) return SNAPPY_B200_BAD_ARGUMENT;
+    if (total_len > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;
+    if (shard_len > total_len) return SNAPPY_B200_BAD_ARGUMENT;
+    if (out_cap < snappy_b200_max_compressed_length(shard_len)) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    u64 total = 0;
+    int rc = compress_shard_locked(g_ctx, d_shard, shard_len, total_len, d_out, 0, &total, nullptr,
+                                   d_frag_sizes, (cudaStream_t)stream);
+    if (rc == SNAPPY_B200_OK) *out_len = (size_t)total;
+    return rc;
+}
+
+int snappy_b200_uncompress_shard_device(const uint8_t* d_in, const uint64_t* d_frag_offsets,
+                                        size_t nfrag, uint8_t* d_out, size_t out_len, void* stream) {
+    if (!d_in || !d_frag_offsets || (!d_out && out_len)) return SNAPPY_B200_BAD_ARGUMENT;
+    if (nfrag != (out_len + kBlockSize - 1) / kBlockSize) return SNAPPY_B200_BAD_ARGUMENT;
+    if (nfrag == 0) return SNAPPY_B200_OK;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    c.last_launches[1] = 0;
+    // the shard's own first/last offsets bound its element bytes
+    u64* h = (u64*)((u8*)c.pinned + 512);
+    CU(cudaMemcpyAsync(h, d_frag_offsets, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + 1, d_frag_offsets + nfrag, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    const u32 grid = ((u32)nfrag + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
+    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_frag_offsets, (u32)nfrag, h[0],
+                                                                 h[1], d_out, (u64)out_len, res);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[3], st));
+        c.ev_pending[1] = true;
+    }
+    c.last_launches[1] = 1;
+    CU(cudaGetLastError());
+    DecodeResult* hr = (DecodeResult*)((u8*)c.pinned + 128);
+    CU(cudaMemcpyAsync(hr, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 1);
+    // a shard has no stream-order context for exact error attribution
+    return hr->fallback ? SNAPPY_B200_INVALID_INPUT : SNAPPY_B200_OK;
+}
+
+int snappy_b200_compress_batched_device(const uint8_t* d_in, const uint64_t* d_in_offsets,
+                                        const uint32_t* d_in_sizes, size_t count, uint8_t* d_out,
+                                        const uint64_t* d_out_offsets, uint32_t* d_out_sizes,
+                                        void* stream) {
+    if (count == 0) return SNAPPY_B200_OK;
+    if (!d_in || !d_in_offsets || !d_in_sizes || !d_out || !d_out_offsets || !d_out_sizes)
+        return SNAPPY_B200_BAD_ARGUMENT;
+    if (count > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the largest page decides the shared-memory footprint (fragment buffer + table)
+    u32* d_max = (u32*)c.result.p;
+    CU(cudaMemsetAsync(d_max, 0, sizeof(DecodeResult), st));
+    k_max_u32<<<(unsigned)((count + 1023) / 1024 < 1024 ? (count + 1023) / 1024 : 1024), 256, 0, st>>>(
+        d_in_sizes, (u32)count, d_max);
+    u32* h = (u32*)((u8*)c.pinned + 640);
+    CU(cudaMemcpyAsync(h, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const u32 max_size = h[0];
+    u32 frag_cap = max_size < kBlockSize ? ((max_size + 15) & ~15u) : kBlockSize;
+    if (frag_cap < 16) frag_cap = 16;
+    u32 entries = 256;
+    while (entries < kMaxTableEntries && entries < max_size) entries <<= 1;
+    const size_t smem = (size_t)frag_cap + kFragPad + (size_t)entries * 2 + 16;
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
+    k_compress_pages<<<(unsigned)count, 32, smem, st>>>(d_in, d_in_offsets, d_in_sizes, d_out,
+                                                        d_out_offsets, d_out_sizes, frag_cap, entries);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[1], st));
+        c.ev_pending[0] = true;
+    }
+    c.last_launches[0] = 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 0);
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_uncompress_batched_device(const uint8_t* d_in, const uint64_t* d_in_offsets,
+                                          const uint32_t* d_in_sizes, size_t count, uint8_t* d_out,
+                                          const uint64_t* d_out_offsets, const uint32_t* d_out_caps,
+                                          uint32_t* d_out_sizes, int32_t* d_statuses, void* stream) {
+    if (count == 0) return SNAPPY_B200_OK;
+    if (!d_in || !d_in_offsets || !d_in_sizes || !d_out || !d_out_offsets || !d_out_caps ||
+        !d_out_sizes || !d_statuses)
+        return SNAPPY_B200_BAD_ARGUMENT;
+    if (count > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    const unsigned grid = (unsigned)((count + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta);
+    k_decode_pages<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_in_offsets, d_in_sizes, (u32)count,
+                                                             d_out, d_out_offsets, d_out_caps,
+                                                             d_out_sizes, d_statuses);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[3], st));
+        c.ev_pending[1] = true;
+    }
+    c.last_launches[1] = 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 1);
+    return SNAPPY_B200_OK;
+}
+
+float snappy_b200_last_kernel_ms(int which) {
+    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    return (which == 0 || which == 1) ? g_ctx.last_ms[which] : 0.f;
+}
+
+int snappy_b200_last_launch_count(int which) {
+    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    return (which == 0 || which == 1) ? g_ctx.last_launches[which] : 0;
+}
+
+void snappy_b200_set_option(const char* name, int value) {
+    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    if (!name) return;
+    if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
+    else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
+    else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
+}
+
+}  // extern "C"

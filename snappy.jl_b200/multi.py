@@ -1,0 +1,150 @@
+"""Multi-GPU sharding of the path on whole-fragment boundaries.
+
+One process per GPU.  A stream of `total_len` bytes is cut into contiguous runs of whole 64 KiB
+fragments, one run per rank (fragments are independent: the hash table is reset per fragment,
+src/Snappy.jl:30, and candidates never precede the fragment start, src/internal.jl:129,190).  The
+only global facts a rank needs are the TOTAL length (table size and header, src/Snappy.jl:26-27)
+and where its bytes go.  The one real exchange step of the path is therefore:
+
+    sizes   = all_gather(compressed byte count of my run)            (8 bytes per rank)
+    offsets = header_len + exclusive_scan(sizes)
+    stream  = segments placed at `offsets` in the owner's buffer      (over NVLink)
+
+`compress_streams` does this for W streams at once (stream s is owned by rank s), which turns the
+assembly into one all_to_all_single with split sizes taken from the gathered size matrix.
+
+The codec calls are injected (`codec`), so the same host logic runs under gloo on CPU tensors in
+the tests (with the oracle as the stand-in codec) and under NCCL with the CUDA path in production.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+FRAGMENT = 65536
+
+
+def shard_bounds(total_len, world):
+    """Byte ranges [lo, hi) of each rank's run of whole fragments; the last run may be ragged."""
+    nfrag = (total_len + FRAGMENT - 1) // FRAGMENT
+    base, extra = divmod(nfrag, world)
+    bounds, f = [], 0
+    for r in range(world):
+        k = base + (1 if r < extra else 0)
+        lo = min(f * FRAGMENT, total_len)
+        hi = min((f + k) * FRAGMENT, total_len)
+        bounds.append((lo, hi))
+        f += k
+    return bounds
+
+
+def encode_header(total_len):
+    """varint.jl:46-69 (host)."""
+    out = bytearray()
+    v = int(total_len)
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+class CudaCodec:
+    """Production codec: the shard entry points of libsnappy_b200.so."""
+
+    def compress_shard(self, shard, total_len):
+        from . import device
+        out, sizes = device.compress_shard_device(shard, total_len, want_sizes=True)
+        return out, sizes
+
+    def uncompress_shard(self, data, frag_offsets, out_len):
+        from . import device
+        return device.uncompress_shard_device(data, frag_offsets, out_len)
+
+
+def compress_streams(shards, total_lens, codec, group=None):
+    """shards[s]: this rank's run of stream s (uint8 tensor), total_lens[s]: stream s's total length.
+    len(shards) == world size; stream s is assembled on rank s.
+
+    Returns (stream, frag_index): the complete stream owned by this rank (header + all ranks'
+    segments) and its side index ((nfrag+1) int64 offsets into the stream)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert len(shards) == world == len(total_lens)
+    dev = shards[0].device
+    segs, frag_sizes = [], []
+    for s in range(world):
+        seg, sizes = codec.compress_shard(shards[s], total_lens[s])
+        segs.append(seg)
+        frag_sizes.append(sizes.to(torch.int64))
+    # exchange 1: compressed byte counts (the path's only data-dependent global fact)
+    mine = torch.tensor([int(x.numel()) for x in segs], dtype=torch.int64, device=dev)
+    matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(matrix, mine, group=group)
+    matrix = matrix.view(world, world).cpu()          # matrix[r][s] = bytes rank r made for stream s
+    in_splits = [int(x) for x in matrix[rank]]
+    out_splits = [int(matrix[r][rank]) for r in range(world)]
+    hdr = encode_header(total_lens[rank])
+    stream = torch.empty(len(hdr) + sum(out_splits), dtype=torch.uint8, device=dev)
+    stream[: len(hdr)] = torch.frombuffer(bytearray(hdr), dtype=torch.uint8).to(dev)
+    # exchange 2: segment assembly -- every segment lands at header + exclusive-scan offset
+    send = torch.cat(segs) if world > 1 else segs[0]
+    dist.all_to_all_single(stream[len(hdr):], send, out_splits, in_splits, group=group)
+    # side index of my stream: fragment sizes of every rank's run, in rank order
+    nf_mine = torch.tensor([int(x.numel()) for x in frag_sizes], dtype=torch.int64, device=dev)
+    nf_matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(nf_matrix, nf_mine, group=group)
+    nf_matrix = nf_matrix.view(world, world).cpu()
+    fs_in = [int(x) for x in nf_matrix[rank]]
+    fs_out = [int(nf_matrix[r][rank]) for r in range(world)]
+    all_sizes = torch.empty(sum(fs_out), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(all_sizes, torch.cat(frag_sizes), fs_out, fs_in, group=group)
+    index = torch.empty(all_sizes.numel() + 1, dtype=torch.int64, device=dev)
+    index[0] = len(hdr)
+    index[1:] = len(hdr) + torch.cumsum(all_sizes, 0)
+    return stream, index
+
+
+def uncompress_streams(stream, index, total_len, codec, group=None):
+    """Inverse: the owner of each stream scatters every rank's compressed range; each rank decodes
+    its own run of every stream.  The uncompressed output stays sharded (SURVEY.md section 5:
+    gathering it on one GPU would be NVLink-ingest bound).  Returns the list of decoded runs, one
+    per stream."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = stream.device
+    lens = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens, torch.tensor([total_len], dtype=torch.int64, device=dev), group=group)
+    lens = [int(x) for x in lens.cpu()]
+    idx = index.cpu().numpy()
+    bounds = shard_bounds(total_len, world)
+    frag_lo = [lo // FRAGMENT for lo, _ in bounds] + [(total_len + FRAGMENT - 1) // FRAGMENT]
+    in_splits = [int(idx[frag_lo[r + 1]] - idx[frag_lo[r]]) for r in range(world)]
+    splits_t = torch.tensor(in_splits, dtype=torch.int64, device=dev)
+    matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(matrix, splits_t, group=group)
+    matrix = matrix.view(world, world).cpu()
+    out_splits = [int(matrix[s][rank]) for s in range(world)]
+    hdr = int(idx[0])
+    recv = torch.empty(sum(out_splits), dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(recv, stream[hdr:], out_splits, in_splits, group=group)
+    # the per-fragment offsets of my run of every stream travel the same way
+    rel = []
+    for r in range(world):
+        part = idx[frag_lo[r]: frag_lo[r + 1] + 1] - idx[frag_lo[r]]
+        rel.append(torch.from_numpy(np.ascontiguousarray(part)).to(dev))
+    n_in = [int(x.numel()) for x in rel]
+    n_mat = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(n_mat, torch.tensor(n_in, dtype=torch.int64, device=dev), group=group)
+    n_mat = n_mat.view(world, world).cpu()
+    n_out = [int(n_mat[s][rank]) for s in range(world)]
+    offs = torch.empty(sum(n_out), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(offs, torch.cat(rel), n_out, n_in, group=group)
+    runs, a, b = [], 0, 0
+    for s in range(world):
+        lo, hi = shard_bounds(lens[s], world)[rank]
+        data = recv[a: a + out_splits[s]]
+        fo = offs[b: b + n_out[s]].contiguous()
+        runs.append(codec.uncompress_shard(data, fo, hi - lo))
+        a += out_splits[s]
+        b += n_out[s]
+    return runs

@@ -1,0 +1,100 @@
+"""CPU suite, part 2: the C-ABI library loads, exports every symbol include/snappy_b200.h declares,
+its host-only helpers agree with the reference's tests, and -- with no GPU -- every compute entry
+point refuses loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from test_oracle import FML_KATS
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "snappy_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(snappy_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(snappy):
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    lib = ctypes.CDLL(snappy._abi.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libsnappy_b200.so does not export %s" % s
+    # and the Python binding table covers exactly the header
+    assert sorted(snappy._abi.SIGNATURES) == syms
+
+
+def test_library_does_not_link_oracle():
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(ROOT, "snappy.jl_b200", "libsnappy_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    nm = subprocess.run(["nm", "-D", os.path.join(ROOT, "snappy.jl_b200", "libsnappy_b200.so")],
+                        capture_output=True, text=True).stdout
+    assert "sjo_" not in nm
+
+
+def test_maxlength_compressed(snappy):
+    for n in (0, 1, 5, 6, 65536, 10 ** 6, 2 ** 30):
+        assert snappy.maxlength_compressed(n) == 32 + n + n // 6  # src/Snappy.jl:80-82
+
+
+def test_varint_host(snappy):
+    for i in range(31):  # test/runtests.jl:157-163
+        enc = snappy.encode32(1 << i)
+        assert snappy.parse32(enc, 0) == (1 << i, len(enc))
+    assert snappy.length_uncompressed(bytes([0xA0, 0x8D, 0x06, 0x00])) == (100000, 3)
+    for bad in (bytes([0xF0]), bytes([0x80, 0x80, 0x80, 0x80, 0x80, 0x0A]),
+                bytes([0xFB, 0xFF, 0xFF, 0xFF, 0x7F]), b""):
+        with pytest.raises(snappy.SnappyError) as e:  # test/runtests.jl:101-111
+            snappy.parse32(bad, 0)
+        assert str(e.value) == "Could not decode varint32."
+
+
+@pytest.mark.parametrize("a,b,limit,want", FML_KATS)
+def test_find_match_length_host(snappy, a, b, limit, want):  # test/runtests.jl:176-267
+    c = (a + b).encode("latin-1")
+    assert snappy.find_match_length(c, 0, len(a), len(a) + limit) == want
+
+
+def test_status_strings(snappy):
+    msgs = {1: "Input too large.", 2: "Invalid input.", 3: "Invalid input: corrupt copy offset",
+            4: "Invalid input: corrupt copy length", 5: "Invalid input: corrupt literal",
+            6: "Could not decode varint32."}
+    for code, msg in msgs.items():
+        assert snappy._abi.status_string(code) == msg
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback(snappy):
+    with pytest.raises(snappy.SnappyError) as e:
+        snappy.compress(b"no gpu here, so this must fail")
+    assert e.value.status == snappy._abi.NO_DEVICE
+    with pytest.raises(snappy.SnappyError) as e:
+        snappy.uncompress(b"\x03\x08abc")
+    assert e.value.status == snappy._abi.NO_DEVICE
+    # the varint is still checked on the host first, as in src/Snappy.jl:47
+    with pytest.raises(snappy.SnappyError) as e:
+        snappy.uncompress(bytes([0xF0]))
+    assert e.value.status == snappy._abi.BAD_VARINT
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "snappy.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in text and "snappy_oracle" not in text and "liboracle" not in text, f

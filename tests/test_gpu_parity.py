@@ -1,0 +1,259 @@
+"""GPU suite: the parity tests proper.  Everything goes through the C ABI of libsnappy_b200.so
+(host-buffer and device-resident entry points) and is compared with the CPU oracle on the same
+inputs -- bit-exact, both directions."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import (ALL_FILES, corrupt_streams, dictionary_fuzz, edge_inputs, read_data)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(snappy):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from snappy_jl_b200 import device
+    return device
+
+
+def to_dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", ALL_FILES)
+def test_files_bit_exact(snappy, oracle, golden, name):  # test/runtests.jl:6-33 + byte parity
+    raw = read_data(name)
+    c = snappy.compress(raw)
+    assert c == oracle.compress(raw)
+    g = golden["files"][name]
+    assert len(c) == g["comp_len"] and hashlib.sha256(c).hexdigest() == g["comp_sha256"]
+    assert snappy.uncompress(c) == raw            # round trip on the GPU
+    assert oracle.uncompress(c) == raw            # GPU stream decodes on the reference path
+    assert c != raw
+
+
+def test_edges_bit_exact(snappy, oracle, golden):  # test/runtests.jl:125-137 and quirk vectors
+    for name, raw in edge_inputs().items():
+        c = snappy.compress(raw)
+        assert c == oracle.compress(raw), name
+        assert hashlib.sha256(c).hexdigest() == golden["edges"][name]["comp_sha256"], name
+        assert snappy.uncompress(c) == raw, name
+
+
+def test_string_api(snappy, oracle):  # src/Snappy.jl:38
+    s = "héllo wörld " * 50
+    assert snappy.compress(s) == oracle.compress(s.encode("utf-8"))
+    assert snappy.uncompress(snappy.compress(s)).decode("utf-8") == s
+
+
+def test_dictionary_fuzz(snappy, oracle):  # test/runtests.jl:35-60
+    for raw in dictionary_fuzz(21, 24):
+        c = snappy.compress(raw)
+        assert c == oracle.compress(raw)
+        assert snappy.uncompress(c) == raw
+
+
+def test_size_sweep(snappy, oracle):
+    rng = np.random.default_rng(17)
+    sizes = list(range(0, 40)) + [59, 60, 61, 62, 255, 256, 257, 1023, 1024, 1025, 4095, 4096, 4097,
+                                  16383, 16384, 16385, 65520, 65521, 65535, 65536, 65537, 65550, 65551,
+                                  65552, 131071, 131072, 131073, 200000]
+    for size in sizes:
+        for alpha in (2, 3, 256):
+            raw = rng.integers(0, alpha, size, dtype=np.uint8).tobytes()
+            c = snappy.compress(raw)
+            assert c == oracle.compress(raw), (size, alpha)
+            assert snappy.uncompress(c) == raw, (size, alpha)
+
+
+def test_max_blowup(snappy, oracle):  # test/runtests.jl:148-154
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 2 ** 32, 20000, dtype=np.uint32).view(np.uint8)
+    raw = np.concatenate([raw, raw[::-1]]).tobytes()
+    c = snappy.compress(raw)
+    assert c == oracle.compress(raw)
+    assert snappy.uncompress(c) == raw
+
+
+def test_must_throw_same_status_as_reference(snappy, oracle):  # test/runtests.jl:62-123
+    for name, stream in corrupt_streams(oracle):
+        want = oracle.status_of_uncompress(stream)
+        assert want != oracle.OK
+        with pytest.raises(snappy.SnappyError) as e:
+            snappy.uncompress(stream)
+        assert e.value.status == want, name
+        assert str(e.value) == oracle.MESSAGES[want], name
+
+
+def test_decoder_quirks(snappy):
+    assert snappy.uncompress(bytes([0x00, 0x00])) == b""
+    assert snappy.uncompress(bytes([0x01, 0x00, 0x41, 0x77])) == b"A"
+
+
+def test_mutation_fuzz_status_parity(snappy, oracle):
+    """flip bytes of valid streams: GPU decoder's status / output must equal the oracle's"""
+    rng = np.random.default_rng(99)
+    bases = [oracle.compress(read_data("sample-tweet.json")), oracle.compress(read_data("html")[:30000]),
+             oracle.compress(b"abcd" * 3000 + bytes(range(256)) * 4)]
+    for base in bases:
+        for _ in range(60):
+            s = bytearray(base)
+            for _k in range(rng.integers(1, 4)):
+                s[rng.integers(1, len(s))] = rng.integers(0, 256)
+            if rng.integers(0, 4) == 0:
+                s = s[: rng.integers(2, len(s))]
+            s = bytes(s)
+            want = oracle.status_of_uncompress(s)
+            if want == oracle.OK:
+                assert snappy.uncompress(s) == oracle.uncompress(s)
+            else:
+                with pytest.raises(snappy.SnappyError) as e:
+                    snappy.uncompress(s)
+                assert e.value.status == want
+
+
+def test_foreign_streams(snappy, oracle):
+    # 32 KiB-block encoder output shipped with the reference (unreferenced fixture)
+    assert snappy.uncompress(read_data("alice29.snappy")) == read_data("alice29.txt")
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    for name in ("html_x_4", "urls.10K", "kppkn.gtb"):
+        raw = read_data(name)
+        theirs = codec.compress(raw).to_pybytes()
+        assert snappy.uncompress(theirs) == raw
+        ours = snappy.compress(raw)
+        assert codec.decompress(ours, decompressed_size=len(raw)).to_pybytes() == raw
+
+
+def test_hand_made_streams(snappy, oracle):
+    # 4-byte-offset copy (never emitted by Snappy.jl, decoder accepts; Appendix A) and overlapping copies
+    lit = bytes([0x0C]) + b"abcd"                       # literal len 4
+    copy4 = bytes([(8 - 1) << 2 | 3]) + (4).to_bytes(4, "little")   # copy len 8 offset 4 (4-byte form)
+    rle = bytes([(64 - 1) << 2 | 2]) + (1).to_bytes(2, "little")     # copy len 64 offset 1
+    body = lit + copy4 + rle
+    s = oracle.encode32(4 + 8 + 64) + body
+    want = oracle.uncompress(s)
+    assert want == b"abcd" * 3 + b"d" * 64
+    assert snappy.uncompress(s) == want
+
+
+def test_device_api_roundtrip_with_index(dev, oracle):
+    import torch
+    from snappy_jl_b200 import synth
+    raw = synth.mix(64, seed=5, tail=12345)
+    d = to_dev(raw)
+    stream, index = dev.compress_device(d, want_index=True)
+    want = oracle.compress_np(raw)
+    assert np.array_equal(stream.cpu().numpy(), want)
+    idx = index.cpu().numpy()
+    nfrag = dev.nfragments(raw.size)
+    assert idx.shape[0] == nfrag + 1 and idx[-1] == want.size and idx[0] == len(oracle.encode32(raw.size))
+    _, sizes = oracle.compress_fragments(raw, raw.size, 0, nfrag)
+    assert np.array_equal(np.diff(idx), sizes.astype(np.int64))
+    back = dev.uncompress_device(stream, index=index, claimed=raw.size)
+    assert torch.equal(back, d)
+    back2 = dev.uncompress_device(stream)  # no side index: segmented speculative parse
+    assert torch.equal(back2, d)
+    # a wrong index must not change the result
+    bad = index.clone()
+    bad[3] += 1
+    back3 = dev.uncompress_device(stream, index=bad, claimed=raw.size)
+    assert torch.equal(back3, d)
+
+
+def test_shard_api(dev, oracle):
+    from snappy_jl_b200 import synth
+    import torch
+    raw = synth.mix(40, seed=9, tail=777)
+    total = raw.size
+    whole = oracle.compress_np(raw)
+    hdr = oracle.encode32(total)
+    cuts = [0, 7 * 65536, 19 * 65536, total]
+    parts, all_sizes = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        out, sizes = dev.compress_shard_device(to_dev(raw[a:b]), total, want_sizes=True)
+        parts.append(out.cpu().numpy())
+        all_sizes.append(sizes.cpu().numpy())
+    assert hdr + b"".join(p.tobytes() for p in parts) == whole.tobytes()
+    # decode each shard from its own element bytes
+    for (a, b), p, s in zip(zip(cuts[:-1], cuts[1:]), parts, all_sizes):
+        offs = np.concatenate([[0], np.cumsum(s.astype(np.int64))])
+        got = dev.uncompress_shard_device(to_dev(p), to_dev(offs), b - a)
+        assert np.array_equal(got.cpu().numpy(), raw[a:b])
+
+
+def test_small_total_uses_small_table(snappy, oracle):
+    # table size comes from the TOTAL length (src/Snappy.jl:27): 256..16384 entries
+    rng = np.random.default_rng(2)
+    for n in (100, 300, 600, 1500, 3000, 6000, 12000, 20000):
+        raw = rng.integers(0, 3, n, dtype=np.uint8).tobytes()
+        assert snappy.compress(raw) == oracle.compress(raw), n
+
+
+def test_batched_pages(dev, oracle):
+    import torch
+    from snappy_jl_b200 import synth
+    count, page = 512, 4096
+    pages = synth.pages(count, page, seed=4)
+    # ragged sizes as well: shrink some pages
+    rng = np.random.default_rng(1)
+    sizes = np.full(count, page, dtype=np.int32)
+    sizes[rng.integers(0, count, 64)] = rng.integers(0, page, 64)
+    offs = (np.arange(count, dtype=np.int64) * page)
+    d = to_dev(pages.reshape(-1))
+    out, out_offs, out_sizes = dev.compress_batched_device(d, to_dev(offs), to_dev(sizes))
+    out_h, oo, os_ = out.cpu().numpy(), out_offs.cpu().numpy(), out_sizes.cpu().numpy()
+    for i in range(count):
+        want = oracle.compress_np(pages[i, : sizes[i]])
+        got = out_h[oo[i]: oo[i] + os_[i]]
+        assert np.array_equal(got, want), i
+    back = torch.zeros(count * page, dtype=torch.uint8, device="cuda")
+    caps = to_dev(np.full(count, page, dtype=np.int32))
+    got_sizes, statuses = dev.uncompress_batched_device(out, out_offs, out_sizes, back, to_dev(offs), caps)
+    assert int(statuses.abs().sum().item()) == 0
+    assert np.array_equal(got_sizes.cpu().numpy(), sizes)
+    bh = back.cpu().numpy().reshape(count, page)
+    for i in range(count):
+        assert np.array_equal(bh[i, : sizes[i]], pages[i, : sizes[i]]), i
+
+
+def test_mix_64mib_bit_exact(dev, oracle):
+    import torch
+    from snappy_jl_b200 import synth
+    raw = synth.mix(1024, seed=2026)
+    d = to_dev(raw)
+    stream, index = dev.compress_device(d, want_index=True)
+    want = oracle.compress_np(raw)
+    assert stream.numel() == want.size
+    assert np.array_equal(stream.cpu().numpy(), want)
+    assert torch.equal(dev.uncompress_device(stream, index=index, claimed=raw.size), d)
+    # config 3: the reference-produced stream, no side index
+    assert torch.equal(dev.uncompress_device(to_dev(want)), d)
+
+
+def test_full_size_1gib_properties(dev, oracle):
+    """BASELINE config 2 at full size: round trip, and bit-exactness of sampled fragments through
+    the side index (the whole-stream oracle compare runs at 64 MiB above)."""
+    import torch
+    from snappy_jl_b200 import synth
+    nfrag = 16384
+    raw = synth.mix(nfrag, seed=2026)
+    d = to_dev(raw)
+    stream, index = dev.compress_device(d, want_index=True)
+    idx = index.cpu().numpy()
+    assert idx[0] == 5 and idx[-1] == stream.numel()
+    assert bytes(stream[:5].cpu().numpy()) == bytes([0x80, 0x80, 0x80, 0x80, 0x04])
+    sh = stream.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for f in np.concatenate([[0, nfrag - 1], rng.integers(0, nfrag, 200)]):
+        want, _ = oracle.compress_fragments(raw, raw.size, int(f), 1)
+        assert np.array_equal(sh[idx[f]: idx[f + 1]], want), f
+    back = dev.uncompress_device(stream, index=index, claimed=raw.size)
+    assert torch.equal(back, d)
+    del back
+    back = dev.uncompress_device(stream)  # arbitrary-stream path at full size
+    assert torch.equal(back, d)
