@@ -1,0 +1,320 @@
+// compress_chain.cuh -- K1 (default): lane-speculative fragment compressor, one warp per fragment.
+//
+// What bounds this kernel (measured, profiles/): the reference's algorithm is a serial decision
+// chain of ~4-8 thousand dependent steps per 64 KiB fragment (probe -> candidate -> match length
+// -> next probe, src/internal.jl:162-239), so a fragment advances at the speed of ONE warp's
+// dependent instruction stream, and throughput = (independent fragments in flight per SM) /
+// (cycles per step).  The only per-fragment state that needs low-latency random read/write is the
+// 32 KiB u16 hash table; the fragment bytes are read-only.  So the table lives in shared memory and
+// the fragment is read in place through L1/L2 (the active working set, resident warps x 64 KiB,
+// sits in the 126 MB L2), which lets 6 fragments run per SM instead of the 2 that fit when the
+// fragment is staged in shared memory next to its table.  Warps are persistent and pull fragments
+// from a global counter, so extra warps whose table lives in global memory (L2) can join in.
+//
+// The decisions are exactly the reference's; the lanes only evaluate them ahead of time:
+//   * scan (src/internal.jl:167-194): lane i takes the i-th probe position of the skip sequence; a
+//     probe whose hash equals an earlier lane's sees that lane's position (== the table insert the
+//     reference would have made, :191); the first hit wins; only lanes up to it commit inserts.
+//   * copy chain (:211-239): while the match length is measured (32 bytes per ballot), lane l
+//     pre-evaluates the post-copy probe (:228-238) for end position ip+4+l; the lane of the real
+//     end position supplies candidate and verdict.
+//   * emission (:252-329): (literal, copy) records are parked one per lane and turned into tag
+//     bytes 32 at a time with a warp prefix sum for the output positions.
+#pragma once
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr u32 kChainPoEntries = 352;  // probe offsets of the skip heuristic (:162-172)
+constexpr u32 kPrefetchLanes = 8;       // post-copy candidates prefetched into L1 (ends ip+4 .. ip+11)
+constexpr u32 kTailPad = 256;         // zero bytes behind the padded copy of the shard's last fragment
+
+// unaligned little-endian 32-bit load through the read-only path (fastmemory.jl:4 load32u);
+// touches the two aligned words around p, i.e. up to 7 bytes past p
+__device__ __forceinline__ u32 ldg32u(const u8* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (u32)a << 3);
+}
+
+template <bool kSmemTable>
+struct Chain {
+    const u8* F;     // fragment bytes (global, >= 64 readable bytes past n)
+    u16* T;          // hash table, position per hash, 0 == empty (shared or global)
+    const u32* PO;   // probe offsets (shared)
+    u8* out;         // scratch slot of this fragment
+    u32 n, shift, lane, op, nrec;
+    int lim;
+    u32 r_from, r_len, r_off, r_M;  // lane k parks record k
+
+    __device__ __forceinline__ u32 hash(u32 w) const { return (w * kHashMul) >> shift; }
+    __device__ __forceinline__ u32 tget(u32 h) const {
+        if (kSmemTable) return T[h];
+        return __ldcg(T + h);
+    }
+    __device__ __forceinline__ void tput(u32 h, u32 pos) const {
+        if (kSmemTable) T[h] = (u16)pos;
+        else __stcg(T + h, (u16)pos);
+    }
+
+    // ---- emission ---------------------------------------------------------------------------
+    static __device__ __forceinline__ u32 copy_bytes(u32 off, u32 M) {  // size of emit_copy!, :306-329
+        if (M == 0) return 0;
+        u32 bytes = 0;
+        if (M >= 12) {
+            if (M >= 68) {
+                const u32 k = (M - 4) >> 6;
+                bytes = 3 * k;
+                M -= k << 6;
+            }
+            if (M > 64) {
+                bytes += 3;
+                M -= 60;
+            }
+        }
+        return bytes + ((M < 12 && off < 2048) ? 2u : 3u);
+    }
+    static __device__ __forceinline__ u32 put_op(u8* o, u32 p, u32 off, u32 len) {  // :289-304
+        if (len < 12 && off < 2048) {
+            o[p] = (u8)(1 + ((len - 4) << 2) + ((off >> 3) & 0xe0));
+            o[p + 1] = (u8)off;
+            return p + 2;
+        }
+        const u32 u = 2 + ((len - 1) << 2) + (off << 8);
+        o[p] = (u8)u;
+        o[p + 1] = (u8)(u >> 8);
+        o[p + 2] = (u8)(u >> 16);
+        return p + 3;
+    }
+
+    __device__ __forceinline__ void flush() {
+        const bool mine = lane < nrec;
+        const u32 lf = r_from, ll = mine ? r_len : 0u, off = r_off, M = mine ? r_M : 0u;
+        // :271-283 header bytes of the literal (a 60-byte literal already takes the long form)
+        const u32 lh = (ll == 0) ? 0u : (ll < 60 ? 1u : ((ll - 1) <= 0xffu ? 2u : ((ll - 1) <= 0xffffu ? 3u : 4u)));
+        const u32 sz = lh + ll + copy_bytes(off, M);
+        u32 incl = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (u32)d) incl += t;
+        }
+        const u32 pos = op + incl - sz;
+        op += __shfl_sync(kFullMask, incl, 31);
+        if (ll) {
+            const u32 nm1 = ll - 1;
+            if (ll < 60) {
+                out[pos] = (u8)(nm1 << 2);
+            } else {
+                out[pos] = (u8)((59 + (lh - 1)) << 2);
+                out[pos + 1] = (u8)nm1;
+                if (lh > 2) out[pos + 2] = (u8)(nm1 >> 8);
+                if (lh > 3) out[pos + 3] = (u8)(nm1 >> 16);
+            }
+            if (ll <= 16) {
+                for (u32 k = 0; k < ll; k++) out[pos + lh + k] = __ldg(F + lf + k);
+            }
+        }
+        u32 lm = __ballot_sync(kFullMask, ll > 16);  // long literals: whole warp, one after the other
+        while (lm) {
+            const u32 j = (u32)__ffs((int)lm) - 1u;
+            lm &= lm - 1;
+            const u32 src = __shfl_sync(kFullMask, lf, j);
+            const u32 len = __shfl_sync(kFullMask, ll, j);
+            const u32 dst = __shfl_sync(kFullMask, pos + lh, j);
+            for (u32 k = lane; k < len; k += 32) out[dst + k] = __ldg(F + src + k);
+        }
+        if (M) {  // :306-329
+            u32 p = pos + lh + ll, len = M;
+            if (len >= 12) {
+                while (len >= 68) {
+                    p = put_op(out, p, off, 64);
+                    len -= 64;
+                }
+                if (len > 64) {
+                    p = put_op(out, p, off, 60);
+                    len -= 60;
+                }
+            }
+            put_op(out, p, off, len);
+        }
+        nrec = 0;
+    }
+
+    __device__ __forceinline__ void keep(u32 from, u32 len, u32 off, u32 M) {
+        if (lane == nrec) {
+            r_from = from;
+            r_len = len;
+            r_off = off;
+            r_M = M;
+        }
+        if (++nrec == 32) flush();
+    }
+
+    // ---- one scan round over 32 probes (lane i = i-th probe of the round) ------------------------
+    // returns 1 = hit (ip/cand set), 2 = bail to the remainder, 0 = no hit (all 32 inserted)
+    __device__ __forceinline__ int scan_round(u32 p, u32 pn, u32& ip, u32& cand) {
+        const bool valid = (int)pn <= lim;  // :175 (checked before probing p)
+        const u32 W = ldg32u(F + (valid ? p : 0u));
+        const u32 H = hash(W);
+        const u32 mp = __match_any_sync(kFullMask, valid ? H : (0x80000000u | lane));
+        u32 c = tget(valid ? H : 0u);
+        // forwarding: the latest earlier probe with the same hash is what the table would hold (:191)
+        const u32 prior = mp & ((1u << lane) - 1u);
+        const u32 j = 31u - (u32)__clz((int)(prior | 1u));
+        const u32 fp = __shfl_sync(kFullMask, p, j);
+        if (prior) c = fp;
+        const bool eq = valid && (ldg32u(F + c) == W);  // :193
+        const u32 hitm = __ballot_sync(kFullMask, eq);
+        const u32 invm = __ballot_sync(kFullMask, !valid);
+        const u32 fh = hitm ? (u32)__ffs((int)hitm) - 1u : 32u;
+        const u32 fi = invm ? (u32)__ffs((int)invm) - 1u : 32u;
+        if (fh >= fi && fi < 32) return 2;
+        const u32 last = (fh < 32) ? fh : 31u;
+        const u32 upto = (last >= 31) ? kFullMask : ((2u << last) - 1u);
+        const u32 after = (lane >= 31) ? 0u : ~((2u << lane) - 1u);
+        // commit inserts of probes 0..last; on equal hashes the later probe wins (:191)
+        if (lane <= last && (mp & after & upto) == 0) tput(H, p);
+        __syncwarp();
+        if (fh < 32) {
+            ip = __shfl_sync(kFullMask, p, fh);
+            cand = __shfl_sync(kFullMask, c, fh);
+            return 1;
+        }
+        return 0;
+    }
+
+    // ---- the fragment --------------------------------------------------------------------------
+    __device__ __forceinline__ void run() {
+        op = 0;
+        nrec = 0;
+        r_from = r_len = r_off = r_M = 0;
+        lim = (int)n - 16;  // ip_limit, :131
+        u32 ip = 0, lit_from = 0;
+        if (n >= kInputMargin) {
+            bool finished = false;
+            while (!finished) {
+                // ---------------- scan, :162-194
+                const u32 s = ip + 1;
+                u32 cand = 0;
+                int res = scan_round(s + lane, s + lane + 1, ip, cand);  // first 32 probes: stride 1
+                for (u32 base = 32; res == 0; base += 32)
+                    res = scan_round(s + PO[base + lane], s + PO[base + lane + 1], ip, cand);
+                if (res == 2) break;
+                // ---------------- copy chain, :211-239
+                // One candidate-side memory round trip per copy: lane l compares byte l of the
+                // candidate with byte l of ip, which verifies the 4-byte match of the previous
+                // step's probe (:238) and measures the match length (:216) at once.  Meanwhile the
+                // lanes pre-evaluate the post-copy probe (:228-235) for end position ip+4+lane from
+                // ip-side bytes only (L1 hits).
+                bool verified = true;  // a scan hit has compared its 4 bytes already (:193)
+                for (;;) {
+                    const u8* pa = F + cand + lane;
+                    const u8* pb = F + ip + lane;
+                    const u32 neq = __ballot_sync(kFullMask, __ldg(pa) != __ldg(pb));
+                    const u32 e = ip + 4 + lane;
+                    const uintptr_t ea = reinterpret_cast<uintptr_t>(F + e - 1);
+                    const u32* ew = reinterpret_cast<const u32*>(ea & ~(uintptr_t)3);
+                    const u32 elo = __ldg(ew), ehi = __ldg(ew + 1);
+                    const u32 Wme = __funnelshift_r(elo, ehi, (u32)ea << 3);                 // bytes [e-1, e+3)
+                    const u32 We = __funnelshift_rc(elo, ehi, (((u32)ea & 3u) << 3) + 8u);  // bytes [e, e+4)
+                    const u32 He = hash(We), Hme = hash(Wme);
+                    const u32 te = tget(He);
+                    const u32 ce = (Hme == He) ? (e - 1) : te;  // :233 is visible to :234
+                    if (kPrefetchLanes && lane < kPrefetchLanes)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(F + ce));
+                    u32 M = neq ? (u32)__ffs((int)neq) - 1u : 32u;
+                    if (!verified && M < 4) break;  // :238 no match at ip: back to scanning from ip+1
+                    if (M == 32) {                  // long match: keep comparing, 32 bytes per round
+                        while (ip + M < n) {
+                            const u32 nq = __ballot_sync(kFullMask, __ldg(pa + M) != __ldg(pb + M));
+                            if (nq) {
+                                M += (u32)__ffs((int)nq) - 1u;
+                                break;
+                            }
+                            M += 32;
+                        }
+                    }
+                    if (ip + M > n) M = n - ip;  // find_match_length stops at the fragment end (:344-387)
+                    keep(lit_from, ip - lit_from, ip - cand, M);  // :200,:217
+                    ip += M;
+                    lit_from = ip;
+                    if ((int)ip >= lim) { finished = true; break; }  // :222
+                    u32 c2;
+                    if (M < 36) {
+                        const u32 owner = M - 4;
+                        c2 = __shfl_sync(kFullMask, ce, owner);
+                        if (lane == owner) {
+                            tput(Hme, ip - 1);  // :233
+                            tput(He, ip);       // :235
+                        }
+                    } else {
+                        const u32 hp = hash(ldg32u(F + ip - 1)), hc = hash(ldg32u(F + ip));
+                        c2 = (hp == hc) ? (ip - 1) : tget(hc);  // :233-234
+                        __syncwarp();
+                        if (lane == 0) {
+                            tput(hp, ip - 1);
+                            tput(hc, ip);
+                        }
+                    }
+                    __syncwarp();
+                    cand = c2;
+                    verified = false;
+                }
+            }
+        }
+        if (lit_from < n) keep(lit_from, n - lit_from, 0, 0);  // :242-248
+        if (nrec) flush();
+    }
+};
+
+// Persistent warps: one CTA = one warp; fragments are pulled from *counter.
+//   tail_copy : padded copy of the shard's LAST fragment (so reads may run past its end)
+//   gtables   : kSmemTable == false: one 32 KiB table per CTA in global memory
+template <bool kSmemTable>
+__global__ void __launch_bounds__(32)
+k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
+                 const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
+                 u32* __restrict__ counter, u16* __restrict__ gtables) {
+    extern __shared__ __align__(128) u8 smem[];
+    u32* PO = reinterpret_cast<u32*>(smem);
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem + kChainPoEntries * 4)
+                        : gtables + (size_t)blockIdx.x * kMaxTableEntries;
+    const u32 lane = lane_id();
+    if (lane == 0) {
+        u32 skip = 32, off = 0;
+        PO[0] = 0;
+        for (u32 i = 1; i < kChainPoEntries; i++) {
+            const u32 b = skip >> 5;
+            skip += b;
+            off = (off + b > 0x100000u) ? 0x100000u : off + b;
+            PO[i] = off;
+        }
+    }
+    __syncwarp();
+    const u32 entries = 1u << (32 - shift);
+    for (;;) {
+        u32 frag = 0;
+        if (lane == 0) frag = atomicAdd(counter, 1u);
+        frag = __shfl_sync(kFullMask, frag, 0);
+        if (frag >= nfrag) break;
+        const u64 start = (u64)frag * kBlockSize;
+        const u32 n = (u32)((shard_len - start < kBlockSize) ? (shard_len - start) : kBlockSize);
+        uint4* t4 = reinterpret_cast<uint4*>(T);
+        for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        Chain<kSmemTable> ch;
+        ch.F = (frag == nfrag - 1) ? tail_copy : g_in + start;
+        ch.T = T;
+        ch.PO = PO;
+        ch.out = scratch + (u64)frag * kSlotStride;
+        ch.n = n;
+        ch.shift = shift;
+        ch.lane = lane;
+        ch.run();
+        if (lane == 0) frag_sizes[frag] = ch.op;
+        __syncwarp();
+    }
+}
+
+}  // namespace sb200

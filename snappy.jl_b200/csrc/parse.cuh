@@ -1,17 +1,33 @@
 // parse.cuh -- segmented speculative parse of an arbitrary Snappy stream (no side index).
 //
-// The tag chain of a stream is serial (each element's position depends on every earlier one).
-// The stream is cut into fixed chunks of compressed bytes, one THREAD per chunk.  Round 0 guesses
-// each chunk's entry (first element start at or after the chunk start) by walking from a
-// look-back position -- tag chains started at different bytes merge quickly -- and parses the chunk
-// from the guess.  k_link_chunks then compares every entry with the predecessor's exit; chunks
-// whose entry was wrong are re-parsed, until nothing changes (at the fixpoint entry[0] is exact and
-// entry[k+1] == exit[k], i.e. the chain is the true one no matter how bad the guesses were).
-// An exclusive scan of the per-chunk output sizes gives each chunk's output offset, and
-// k_build_index records the compressed position of every 64 KiB output boundary.  If the stream is
-// "fragment-clean" (no element straddles, no copy reaches across a 64 KiB output boundary -- true
-// for everything Snappy.jl and libsnappy emit) the result is the same side index the compressor
-// produces, and the indexed decoder runs.  Anything else is left to the exact serial decoder.
+// The tag chain of a stream is serial: each element's position depends on every earlier one
+// (loop header of decompress_all_tags!, src/internal.jl:416-439).  It is cut into fixed chunks of
+// compressed bytes, one THREAD per chunk, and recovered in a fixed number of parallel passes:
+//
+//  A  k_parse_guess   every chunk guesses its entry by walking from a look-back position (tag chains
+//                     started at different bytes merge within a few elements) and parses itself:
+//                     first[k] = first visited position >= chunk start, exit[k] = first visited
+//                     position >= chunk end.  Chunks inside long literals produce garbage; that
+//                     is harmless because nothing below trusts a chunk before it is REACHED.
+//  B  k_parse_bridge  for every chunk k: where does the chain go if exit[k] is a real element
+//                     start?  Normally exit[k] == first[j] of the chunk j it lands in (join).
+//                     Otherwise (a long literal ended inside j and j's guess started in its bytes)
+//                     the thread walks on from exit[k] ("bridge", at most kBridgeBudget elements;
+//                     a 64 KiB literal is one element) until its first element start in some
+//                     chunk equals that chunk's first[].  next[k] = joined chunk.
+//  C  k_parse_reach   chunk 0 starts exactly behind the varint, so it is real; pointer doubling
+//                     over next[] marks every chunk the real chain reaches (log2(nchunk) rounds).
+//  D  k_parse_entries real entry of a reached chunk = first[k]; reached chunks re-walk their bridge
+//                     and give every chunk it enters its real entry; all other chunks hold no
+//                     element start.
+//  E  k_parse_final   every real chunk is parsed once more from its real entry: output bytes,
+//                     anomaly flags.  A scan gives output offsets, k_build_index records the
+//                     compressed position of every 64 KiB output boundary.
+//
+// If the stream is "fragment-clean" (no element straddles, no copy reaches across a 64 KiB output
+// boundary -- true for everything Snappy.jl emits) the result is the side index the compressor
+// would have produced and the indexed decoder runs; it re-validates every fragment, so a wrong
+// index can only cost time, never change the result.  Anything else goes to the exact decoder.
 #pragma once
 #include "common.cuh"
 #include "decompress.cuh"
@@ -21,16 +37,36 @@ namespace sb200 {
 constexpr u32 kParseChunk = 4096;     // compressed bytes per chunk
 constexpr u32 kParseLookback = 1024;  // guess walk starts this far before the chunk
 constexpr u32 kParseThreads = 128;
+constexpr u32 kBridgeBudget = 20000;  // elements a bridge may walk before it gives up
+constexpr u64 kDeadPos = ~0ull;
+constexpr u32 kNextDead = 0xffffffffu;  // chain cannot be followed from here
 
-enum : u32 { PF_ANOMALY = 1u, PF_NOT_CLEAN = 2u, PF_BAD_END = 4u, PF_BAD_TOTAL = 8u };
+enum : u32 { PF_ANOMALY = 1u, PF_NOT_CLEAN = 2u, PF_BROKEN = 4u };
 
 struct ParseArrays {
-    u64* entry;   // [nchunk] first element start >= chunk start (under the current chain)
-    u64* exit;    // [nchunk] first element start >= chunk end (== entry of the next chunk)
-    u32* outb;    // [nchunk] output bytes produced by the chunk's elements
-    u32* flags;   // [nchunk] PF_* seen while parsing from `entry`
-    u32* dirty;   // [nchunk] needs a re-parse
-    u32* counters;  // [0] changes made by k_link_chunks, [1] OR of flags, [2] not-clean flag
+    u64* first;         // [nchunk]
+    u64* exit;          // [nchunk]
+    u64* entry;         // [nchunk] real entry (kDeadPos: chunk holds no element start)
+    u32* next_a;        // [nchunk] successor chunk (nchunk = end of stream, kNextDead = dead)
+    u32* next_b;        // [nchunk] double buffer for pointer doubling
+    u32* reach;         // [nchunk]
+    u32* outb;          // [nchunk] output bytes of the chunk's real elements
+    u32* counters;      // [0] OR of PF_* flags
+    static size_t bytes(size_t nchunk) {
+        return nchunk * (8 * 3 + 4 * 4) + 64;
+    }
+    void carve(void* base, size_t nchunk) {
+        u64* p = (u64*)base;
+        first = p; p += nchunk;
+        exit = p; p += nchunk;
+        entry = p; p += nchunk;
+        u32* q = (u32*)p;
+        next_a = q; q += nchunk;
+        next_b = q; q += nchunk;
+        reach = q; q += nchunk;
+        outb = q; q += nchunk;
+        counters = q;
+    }
 };
 
 // one element at ip: returns false on an anomaly (header or literal past the end, empty element)
@@ -48,91 +84,135 @@ __device__ __forceinline__ bool walk_step(const u8* __restrict__ in, u64 L, u64&
     return true;
 }
 
-__global__ void __launch_bounds__(kParseThreads)
-k_parse_chunks(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, int first_round) {
-    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
-    if (k >= nchunk) return;
-    const u64 start = hdr + (u64)k * kParseChunk;
-    const u64 end = (start + kParseChunk < L) ? (start + kParseChunk) : L;
-    u64 ip;
+// walk from ip until the chunk end (or the end of the stream, src/internal.jl:416: `ip + 1 < L`);
+// returns false on an anomaly.  produced accumulates element lengths.
+__device__ __forceinline__ bool walk_chunk(const u8* __restrict__ in, u64 L, u64 end, u64& ip, u64& produced) {
     Element e;
-    if (first_round) {
-        ip = hdr;
-        if (k > 0) {
-            ip = (start - hdr > kParseLookback) ? (start - kParseLookback) : hdr;
-            while (ip < start && ip + 1 < L) {
-                if (!walk_step(in, L, ip, e)) { ip = start; break; }  // garbage: any guess will do
-            }
-            if (ip < start) ip = start;
-        }
-        pa.entry[k] = ip;
-    } else {
-        if (!pa.dirty[k]) return;
-        pa.dirty[k] = 0;
-        ip = pa.entry[k];
-    }
-    u64 produced = 0;
-    u32 flags = 0;
-    while (ip < end && ip + 1 < L) {  // `ip + 1 < L`: src/internal.jl:416
-        if (!walk_step(in, L, ip, e)) {
-            flags |= PF_ANOMALY;
-            ip = L;
-            break;
-        }
+    while (ip < end && ip + 1 < L) {
+        if (!walk_step(in, L, ip, e)) return false;
         produced += e.len;
     }
-    if (produced > 0xffffffffull) {
-        flags |= PF_ANOMALY;
-        produced = 0xffffffffull;
-    }
-    pa.exit[k] = ip;
-    pa.outb[k] = (u32)produced;
-    pa.flags[k] = flags;
+    return true;
 }
 
-// entry[k] must equal exit[k-1]; chunks that the predecessor's last element jumps over entirely
-// (long literals) are resolved on the spot.  counters[0] counts the changes.
-__global__ void __launch_bounds__(256)
-k_link_chunks(u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
-    const u32 k = blockIdx.x * 256 + threadIdx.x + 1;
+__device__ __forceinline__ void chunk_range(u64 hdr, u64 L, u32 k, u64& start, u64& end) {
+    start = hdr + (u64)k * kParseChunk;
+    end = (start + kParseChunk < L) ? (start + kParseChunk) : L;
+}
+
+__global__ void __launch_bounds__(kParseThreads)
+k_parse_guess(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
-    const u64 v = pa.exit[k - 1];
-    if (pa.entry[k] == v) return;
-    pa.entry[k] = v;
-    const u64 start = hdr + (u64)k * kParseChunk;
-    const u64 end = (start + kParseChunk < L) ? (start + kParseChunk) : L;
-    if (v >= end) {
-        pa.exit[k] = v;
-        pa.outb[k] = 0;
-        pa.flags[k] = 0;
-        pa.dirty[k] = 0;
-    } else {
-        pa.dirty[k] = 1;
+    u64 start, end;
+    chunk_range(hdr, L, k, start, end);
+    u64 ip = hdr;
+    Element e;
+    if (k > 0) {
+        ip = (start - hdr > kParseLookback) ? (start - kParseLookback) : hdr;
+        while (ip < start && ip + 1 < L) {
+            if (!walk_step(in, L, ip, e)) { ip = start; break; }  // garbage: any guess will do
+        }
+        if (ip < start) ip = start;
     }
-    atomicAdd(&pa.counters[0], 1u);
+    pa.first[k] = ip;
+    u64 produced = 0;
+    const bool ok = walk_chunk(in, L, end, ip, produced);
+    pa.exit[k] = ok ? ip : kDeadPos;
+    pa.reach[k] = (k == 0) ? 1u : 0u;
 }
 
-// OR of the per-chunk flags, and the chain must end exactly at L (a trailing ignored byte or a
-// truncated header is the exact decoder's business)
+__global__ void __launch_bounds__(kParseThreads)
+k_parse_bridge(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
+    if (k >= nchunk) return;
+    u64 x = pa.exit[k];
+    u32 nx = kNextDead, prev = kNextDead;
+    Element e;
+    for (u32 steps = 0; x != kDeadPos && steps < kBridgeBudget; steps++) {
+        if (x + 1 >= L) { nx = nchunk; break; }  // the chain ends here (a lone trailing byte is ignored)
+        const u32 j = (u32)((x - hdr) / kParseChunk);
+        if (j != prev) {  // x is this chain's first element start in chunk j
+            if (pa.first[j] == x) { nx = j; break; }
+            prev = j;
+        }
+        if (!walk_step(in, L, x, e)) break;
+    }
+    pa.next_a[k] = nx;
+}
+
+// one round of pointer doubling: reach spreads over `nx`, then nx_out = nx o nx
 __global__ void __launch_bounds__(256)
-k_parse_check(u64 L, u32 nchunk, ParseArrays pa) {
-    u32 f = 0;
-    for (u32 k = blockIdx.x * 256 + threadIdx.x; k < nchunk; k += gridDim.x * 256) f |= pa.flags[k];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && pa.exit[nchunk - 1] != L) f |= PF_BAD_END;
-    f = __reduce_or_sync(kFullMask, f);
-    if ((threadIdx.x & 31) == 0 && f) atomicOr(&pa.counters[1], f);
+k_parse_reach(u32 nchunk, const u32* __restrict__ nx, u32* __restrict__ nx_out, u32* reach) {
+    const u32 k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= nchunk) return;
+    const u32 j = nx[k];
+    if (j < nchunk) {
+        if (reach[k]) reach[j] = 1u;
+        nx_out[k] = nx[j];
+    } else {
+        nx_out[k] = j;
+    }
 }
 
-// Walk each chunk again with its output offset known; record the compressed position of every
+// entry[k] of the chunks the real chain touches.  phase 0: reached chunks start at first[k].
+// phase 1: every reached chunk re-walks its bridge (exit[k] .. the join) and gives each chunk the
+// bridge enters its real entry.
+__global__ void __launch_bounds__(kParseThreads)
+k_parse_entries(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
+                const u32* __restrict__ next_orig, int phase) {
+    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
+    if (k >= nchunk) return;
+    if (phase == 0) {
+        pa.entry[k] = pa.reach[k] ? pa.first[k] : kDeadPos;
+        if (pa.reach[k] && next_orig[k] == kNextDead) atomicOr(&pa.counters[0], PF_BROKEN);
+        return;
+    }
+    if (!pa.reach[k] || next_orig[k] == kNextDead) return;
+    u64 x = pa.exit[k];
+    u32 prev = kNextDead;
+    Element e;
+    for (u32 steps = 0; steps < kBridgeBudget; steps++) {
+        if (x + 1 >= L) break;
+        const u32 j = (u32)((x - hdr) / kParseChunk);
+        if (j != prev) {
+            if (pa.first[j] == x) break;  // joined: phase 0 already set entry[j]
+            pa.entry[j] = x;
+            prev = j;
+        }
+        if (!walk_step(in, L, x, e)) break;
+    }
+}
+
+__global__ void __launch_bounds__(kParseThreads)
+k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
+    if (k >= nchunk) return;
+    u64 ip = pa.entry[k];
+    u64 produced = 0;
+    if (ip != kDeadPos) {
+        u64 start, end;
+        chunk_range(hdr, L, k, start, end);
+        if (!walk_chunk(in, L, end, ip, produced) || produced > 0xffffffffull) {
+            atomicOr(&pa.counters[0], PF_ANOMALY);
+            produced = 0;
+        }
+    }
+    pa.outb[k] = (u32)produced;
+}
+
+// Walk each real chunk again with its output offset known; record the compressed position of every
 // element that starts exactly on a 64 KiB output boundary; flag anything not fragment-clean.
 __global__ void __launch_bounds__(kParseThreads)
 k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
               const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
-    const u64 start = hdr + (u64)k * kParseChunk;
-    const u64 end = (start + kParseChunk < L) ? (start + kParseChunk) : L;
+    if (k == 0) index[nfrag] = L;
     u64 ip = pa.entry[k];
+    if (ip == kDeadPos) return;
+    u64 start, end;
+    chunk_range(hdr, L, k, start, end);
     u64 op = out_off[k];
     bool clean = true;
     Element e;
@@ -145,8 +225,7 @@ k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
         if (e.is_copy && e.offset > in_frag) clean = false;
         op += e.len;
     }
-    if (!clean) atomicOr(&pa.counters[2], 1u);
-    if (k == 0) index[nfrag] = L;
+    if (!clean) atomicOr(&pa.counters[0], PF_NOT_CLEAN);
 }
 
 __global__ void __launch_bounds__(256)

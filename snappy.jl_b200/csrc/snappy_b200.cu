@@ -14,6 +14,7 @@
 #include <string>
 
 #include "compress.cuh"
+#include "compress_chain.cuh"
 #include "decompress.cuh"
 #include "parse.cuh"
 
@@ -45,7 +46,9 @@ struct DevBuf {
 };
 
 struct Options {
-    int compress_variant = 0;   // 0 = default
+    int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
+    int smem_chains = 6;        // persistent warps per SM with the table in shared memory
+    int l2_chains = 0;          // extra persistent warps per SM with the table in global memory (L2)
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int timing = 1;             // record CUDA events around the dominant kernel
 };
@@ -56,7 +59,9 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     // scratch for compress
-    DevBuf scratch, frag_sizes, frag_offsets;
+    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables;
+    cudaStream_t side = nullptr;      // second stream for the global-table warps
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for decode
     DevBuf result, parse_a, parse_b, parse_c, index;
     // staging for the host-buffer API
@@ -117,9 +122,16 @@ int ctx_init_locked(int device) {
                             (int)kCompressSmemBytes));
     CU(cudaFuncSetAttribute(k_compress_pages, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompressSmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompress2SmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kChainPoEntries * 4 + kMaxTableEntries * 2)));
+    CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CU(cudaMallocHost(&c.pinned, 4096));
     for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
-    CU(c.result.ensure(sizeof(DecodeResult)));
+    CU(c.result.ensure(256));
     c.ready = true;
     return SNAPPY_B200_OK;
 }
@@ -192,16 +204,51 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
     u32* sizes = (u32*)c.frag_sizes.p;
     u64* offs = (u64*)c.frag_offsets.p;
 
-    if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
-    k_compress_fragments_serial<<<nfrag, 32, kCompressSmemBytes, st>>>(d_in, (u64)shard_len, shift,
-                                                                      scratch, sizes);
+    int launches = 0;
+    if (c.opt.compress_variant == 0) {
+        // padded copy of the last fragment (the chain kernel reads a few bytes past a fragment's end)
+        const u64 tail_start = (u64)(nfrag - 1) * kBlockSize;
+        const size_t tail_len = shard_len - tail_start;
+        CU(c.tail.ensure(kBlockSize + kTailPad + 16));
+        CU(cudaMemcpyAsync(c.tail.p, d_in + tail_start, tail_len, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemsetAsync((u8*)c.tail.p + tail_len, 0, kTailPad, st));
+        u32* counter = (u32*)((u8*)c.result.p + 64);
+        CU(cudaMemsetAsync(counter, 0, 4, st));
+        const u32 want_a = (u32)c.sm_count * (u32)c.opt.smem_chains;
+        const u32 grid_a = nfrag < want_a ? nfrag : want_a;
+        const u32 grid_b = (nfrag > grid_a) ? (u32)c.sm_count * (u32)c.opt.l2_chains : 0u;
+        if (grid_b) CU(c.gtables.ensure((size_t)grid_b * kMaxTableEntries * 2));
+        if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
+        if (grid_b) CU(cudaEventRecord(c.ev_fork, st));
+        k_compress_chain<true><<<grid_a, 32, kChainPoEntries * 4 + kMaxTableEntries * 2, st>>>(
+            d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr);
+        launches = 1;
+        if (grid_b) {
+            CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+            k_compress_chain<false><<<grid_b, 32, kChainPoEntries * 4, c.side>>>(
+                d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
+                (u16*)c.gtables.p);
+            CU(cudaEventRecord(c.ev_join, c.side));
+            CU(cudaStreamWaitEvent(st, c.ev_join, 0));
+            launches = 2;
+        }
+    } else {
+        if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
+        if (c.opt.compress_variant == 1)
+            k_compress_fragments_serial<<<nfrag, 32, kCompressSmemBytes, st>>>(d_in, (u64)shard_len, shift,
+                                                                              scratch, sizes);
+        else
+            k_compress_fragments<<<nfrag, 64, kCompress2SmemBytes, st>>>(d_in, (u64)shard_len, shift,
+                                                                        scratch, sizes);
+        launches = 1;
+    }
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[1], st));
         c.ev_pending[0] = true;
     }
     k_scan_sizes<<<1, 1024, 0, st>>>(sizes, nfrag, base, offs);
     k_compact<<<nfrag, 256, 0, st>>>(scratch, sizes, offs, d_out);
-    c.last_launches[0] = 3;
+    c.last_launches[0] = launches + 2;
     CU(cudaGetLastError());
     u64* h = (u64*)c.pinned;
     CU(cudaMemcpyAsync(h, offs + nfrag, 8, cudaMemcpyDeviceToHost, st));
@@ -274,60 +321,60 @@ int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 cla
     const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
     if (nfrag == 0 || n <= hdr) return -1;
     const u64 body = n - hdr;
-    if (body / kParseChunk >= 0x7fffffffull) return -1;
+    if (body / kParseChunk >= 0x7ffffff0ull) return -1;
     const u32 nchunk = (u32)((body + kParseChunk - 1) / kParseChunk);
-    CU(c.parse_a.ensure((size_t)nchunk * 16));               // entry, exit
-    CU(c.parse_b.ensure((size_t)nchunk * 12 + 64));          // outb, flags, dirty, counters
-    CU(c.parse_c.ensure(((size_t)nchunk + 1) * 8));          // output offsets
+    CU(c.parse_a.ensure(ParseArrays::bytes(nchunk)));
+    CU(c.parse_c.ensure(((size_t)nchunk + 1) * 8));  // output offsets
     CU(c.index.ensure(((size_t)nfrag + 1) * 8));
     ParseArrays pa;
-    pa.entry = (u64*)c.parse_a.p;
-    pa.exit = pa.entry + nchunk;
-    pa.outb = (u32*)c.parse_b.p;
-    pa.flags = pa.outb + nchunk;
-    pa.dirty = pa.flags + nchunk;
-    pa.counters = pa.dirty + nchunk;
+    pa.carve(c.parse_a.p, nchunk);
     u64* out_off = (u64*)c.parse_c.p;
     u32* h = (u32*)((u8*)c.pinned + 1024);
 
-    CU(cudaMemsetAsync(pa.dirty, 0, (size_t)nchunk * 4 + 64, st));
+    CU(cudaMemsetAsync(pa.counters, 0, 64, st));
     const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
     const u32 lgrid = (nchunk + 255) / 256;
-    k_parse_chunks<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, 1);
-    c.last_launches[1] += 1;
-    bool converged = false;
-    for (int round = 0; round < 256 && !converged; round++) {
-        // several link passes per round: a long literal resolves the chunks it jumps over one
-        // pass at a time (a 64 KiB literal spans 16 chunks)
-        for (int s = 0; s < 18; s++) k_link_chunks<<<lgrid, 256, 0, st>>>((u64)n, (u64)hdr, nchunk, pa);
-        c.last_launches[1] += 18;
-        CU(cudaMemcpyAsync(h, pa.counters, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (h[0] == 0) {
-            converged = true;
-        } else {
-            CU(cudaMemsetAsync(pa.counters, 0, 4, st));
-            k_parse_chunks<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, 0);
-            c.last_launches[1] += 1;
-        }
-    }
-    if (!converged) return -1;
-    k_parse_check<<<(lgrid < 1024 ? lgrid : 1024), 256, 0, st>>>((u64)n, nchunk, pa);
-    k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
+    k_parse_guess<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
+    k_parse_bridge<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
     c.last_launches[1] += 2;
+    // pointer doubling: after r rounds everything within 2^r hops of chunk 0 is marked
+    u32* nx = pa.next_a;
+    u32* nx2 = pa.next_b;
+    // keep the original successor array for the broken-chain check: doubling works on copies
+    CU(c.parse_b.ensure((size_t)nchunk * 4));
+    u32* next_orig = (u32*)c.parse_b.p;
+    CU(cudaMemcpyAsync(next_orig, pa.next_a, (size_t)nchunk * 4, cudaMemcpyDeviceToDevice, st));
+    for (u32 span = 1; span < nchunk; span <<= 1) {
+        k_parse_reach<<<lgrid, 256, 0, st>>>(nchunk, nx, nx2, pa.reach);
+        u32* t = nx;
+        nx = nx2;
+        nx2 = t;
+        c.last_launches[1] += 1;
+    }
+    k_parse_reach<<<lgrid, 256, 0, st>>>(nchunk, nx, nx2, pa.reach);
+    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 0);
+    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 1);
+    k_parse_final<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
+    k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
+    c.last_launches[1] += 5;
+    CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h + 4, out_off + nchunk, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     u64 total;
     memcpy(&total, h + 4, 8);
-    if (h[1] != 0 || total != claimed) return -1;
+    if (getenv("SNAPPY_B200_DEBUG"))
+        fprintf(stderr, "[snappy_b200] parse: nchunk=%u flags=%u total=%llu claimed=%u\n", nchunk, h[0],
+                (unsigned long long)total, claimed);
+    if (h[0] != 0 || total != claimed) return -1;
     k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off,
                                                   (u64*)c.index.p, nfrag);
     c.last_launches[1] += 1;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    return h[2] ? -1 : 0;
+    if (getenv("SNAPPY_B200_DEBUG")) fprintf(stderr, "[snappy_b200] index: flags=%u\n", h[0]);
+    return h[0] ? -1 : 0;
 }
 
 int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
@@ -407,7 +454,12 @@ void snappy_b200_shutdown(void) {
     Context& c = g_ctx;
     if (!c.ready) return;
     cudaSetDevice(c.device);
-    for (DevBuf* b : {&c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
+    if (c.side) cudaStreamDestroy(c.side);
+    c.side = nullptr;
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    c.ev_fork = c.ev_join = nullptr;
+    for (DevBuf* b : {&c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
                       &c.parse_c, &c.index, &c.stage_in, &c.stage_out})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
@@ -653,6 +705,8 @@ void snappy_b200_set_option(const char* name, int value) {
     if (!name) return;
     if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
+    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value;
+    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value;
     else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
 }
 
