@@ -27,6 +27,7 @@ namespace sb200 {
 
 constexpr u32 kChainPoEntries = 352;  // probe offsets of the skip heuristic (:162-172)
 constexpr u32 kPrefetchLanes = 8;       // post-copy candidates prefetched into L1 (ends ip+4 .. ip+11)
+constexpr u32 kStreamAhead = 2048;     // ip-side bytes are pulled into L2 this far ahead
 constexpr u32 kTailPad = 256;         // zero bytes behind the padded copy of the shard's last fragment
 
 // unaligned little-endian 32-bit load through the read-only path (fastmemory.jl:4 load32u);
@@ -37,23 +38,43 @@ __device__ __forceinline__ u32 ldg32u(const u8* p) {
     return __funnelshift_r(__ldg(w), __ldg(w + 1), (u32)a << 3);
 }
 
+// probe offsets of the skip heuristic (skip starts at 32, step = skip >> 5, :162-172); filled once
+// by k_init_probe_offsets.  Only scan rounds past the first 32 probes read it (incompressible data).
+__device__ u32 g_probe_offsets[kChainPoEntries];
+
+__global__ void k_init_probe_offsets() {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u32 skip = 32, off = 0;
+    g_probe_offsets[0] = 0;
+    for (u32 i = 1; i < kChainPoEntries; i++) {
+        const u32 b = skip >> 5;
+        skip += b;
+        off = (off + b > 0x100000u) ? 0x100000u : off + b;
+        g_probe_offsets[i] = off;
+    }
+}
+
 template <bool kSmemTable>
 struct Chain {
     const u8* F;     // fragment bytes (global, >= 64 readable bytes past n)
-    u16* T;          // hash table, position per hash, 0 == empty (shared or global)
-    const u32* PO;   // probe offsets (shared)
+    u16* T;          // hash table, position per hash, 0 == empty (global variant)
+    u32 Ts;          // shared-space address of the table (shared variant)
     u8* out;         // scratch slot of this fragment
-    u32 n, shift, lane, op, nrec;
+    u32 n, shift, lane, op, nrec, pf_lanes;
     int lim;
-    u32 r_from, r_len, r_off, r_M;  // lane k parks record k
+    u32 r_lit, r_cpy;  // lane k parks record k: literal (from | len << 16), copy (offset | M << 16)
 
     __device__ __forceinline__ u32 hash(u32 w) const { return (w * kHashMul) >> shift; }
     __device__ __forceinline__ u32 tget(u32 h) const {
-        if (kSmemTable) return T[h];
+        if (kSmemTable) {
+            u16 v;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(Ts + 2u * h) : "memory");
+            return v;
+        }
         return __ldcg(T + h);
     }
     __device__ __forceinline__ void tput(u32 h, u32 pos) const {
-        if (kSmemTable) T[h] = (u16)pos;
+        if (kSmemTable) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
         else __stcg(T + h, (u16)pos);
     }
 
@@ -89,7 +110,8 @@ struct Chain {
 
     __device__ __forceinline__ void flush() {
         const bool mine = lane < nrec;
-        const u32 lf = r_from, ll = mine ? r_len : 0u, off = r_off, M = mine ? r_M : 0u;
+        const u32 lf = r_lit & 0xffffu, ll = mine ? (r_lit >> 16) : 0u;
+        const u32 off = r_cpy & 0xffffu, M = mine ? (r_cpy >> 16) : 0u;
         // :271-283 header bytes of the literal (a 60-byte literal already takes the long form)
         const u32 lh = (ll == 0) ? 0u : (ll < 60 ? 1u : ((ll - 1) <= 0xffu ? 2u : ((ll - 1) <= 0xffffu ? 3u : 4u)));
         const u32 sz = lh + ll + copy_bytes(off, M);
@@ -142,11 +164,10 @@ struct Chain {
     }
 
     __device__ __forceinline__ void keep(u32 from, u32 len, u32 off, u32 M) {
+        // len < 65536 here: the only 65536-byte literal is a whole-fragment remainder (see run())
         if (lane == nrec) {
-            r_from = from;
-            r_len = len;
-            r_off = off;
-            r_M = M;
+            r_lit = from | (len << 16);
+            r_cpy = off | (M << 16);
         }
         if (++nrec == 32) flush();
     }
@@ -188,7 +209,7 @@ struct Chain {
     __device__ __forceinline__ void run() {
         op = 0;
         nrec = 0;
-        r_from = r_len = r_off = r_M = 0;
+        r_lit = r_cpy = 0;
         lim = (int)n - 16;  // ip_limit, :131
         u32 ip = 0, lit_from = 0;
         if (n >= kInputMargin) {
@@ -199,7 +220,7 @@ struct Chain {
                 u32 cand = 0;
                 int res = scan_round(s + lane, s + lane + 1, ip, cand);  // first 32 probes: stride 1
                 for (u32 base = 32; res == 0; base += 32)
-                    res = scan_round(s + PO[base + lane], s + PO[base + lane + 1], ip, cand);
+                    res = scan_round(s + g_probe_offsets[base + lane], s + g_probe_offsets[base + lane + 1], ip, cand);
                 if (res == 2) break;
                 // ---------------- copy chain, :211-239
                 // One candidate-side memory round trip per copy: lane l compares byte l of the
@@ -221,8 +242,10 @@ struct Chain {
                     const u32 He = hash(We), Hme = hash(Wme);
                     const u32 te = tget(He);
                     const u32 ce = (Hme == He) ? (e - 1) : te;  // :233 is visible to :234
-                    if (kPrefetchLanes && lane < kPrefetchLanes)
+                    if (lane < pf_lanes)
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(F + ce));
+                    if (lane == 31 && ip + kStreamAhead < n)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(F + ip + kStreamAhead));
                     u32 M = neq ? (u32)__ffs((int)neq) - 1u : 32u;
                     if (!verified && M < 4) break;  // :238 no match at ip: back to scanning from ip+1
                     if (M == 32) {                  // long match: keep comparing, 32 bytes per round
@@ -263,8 +286,23 @@ struct Chain {
                 }
             }
         }
-        if (lit_from < n) keep(lit_from, n - lit_from, 0, 0);  // :242-248
         if (nrec) flush();
+        if (lit_from < n) {  // :242-248 remainder literal (up to the whole fragment: emitted directly)
+            const u32 ll = n - lit_from, nm1 = ll - 1;
+            const u32 lh = ll < 60 ? 1u : (nm1 <= 0xffu ? 2u : (nm1 <= 0xffffu ? 3u : 4u));
+            if (lane == 0) {
+                if (ll < 60) {
+                    out[op] = (u8)(nm1 << 2);
+                } else {
+                    out[op] = (u8)((59 + (lh - 1)) << 2);
+                    out[op + 1] = (u8)nm1;
+                    if (lh > 2) out[op + 2] = (u8)(nm1 >> 8);
+                    if (lh > 3) out[op + 3] = (u8)(nm1 >> 16);
+                }
+            }
+            for (u32 k = lane; k < ll; k += 32) out[op + lh + k] = __ldg(F + lit_from + k);
+            op += lh + ll;
+        }
     }
 };
 
@@ -275,23 +313,10 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(32)
 k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
-                 u32* __restrict__ counter, u16* __restrict__ gtables) {
+                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes) {
     extern __shared__ __align__(128) u8 smem[];
-    u32* PO = reinterpret_cast<u32*>(smem);
-    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem + kChainPoEntries * 4)
-                        : gtables + (size_t)blockIdx.x * kMaxTableEntries;
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) : gtables + (size_t)blockIdx.x * kMaxTableEntries;
     const u32 lane = lane_id();
-    if (lane == 0) {
-        u32 skip = 32, off = 0;
-        PO[0] = 0;
-        for (u32 i = 1; i < kChainPoEntries; i++) {
-            const u32 b = skip >> 5;
-            skip += b;
-            off = (off + b > 0x100000u) ? 0x100000u : off + b;
-            PO[i] = off;
-        }
-    }
-    __syncwarp();
     const u32 entries = 1u << (32 - shift);
     for (;;) {
         u32 frag = 0;
@@ -306,11 +331,12 @@ k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shif
         Chain<kSmemTable> ch;
         ch.F = (frag == nfrag - 1) ? tail_copy : g_in + start;
         ch.T = T;
-        ch.PO = PO;
+        ch.Ts = kSmemTable ? smem_u32(T) : 0u;
         ch.out = scratch + (u64)frag * kSlotStride;
         ch.n = n;
         ch.shift = shift;
         ch.lane = lane;
+        ch.pf_lanes = pf_lanes;
         ch.run();
         if (lane == 0) frag_sizes[frag] = ch.op;
         __syncwarp();

@@ -163,70 +163,111 @@ k_decode_serial(const u8* __restrict__ in, u64 L, u64 ip0, u8* __restrict__ out,
 // Anything that is not a clean, self-contained fragment sets res->fallback and the caller reruns
 // the exact serial decoder, so a wrong index can never change the result.
 constexpr u32 kDecodeWarpsPerCta = 4;
-constexpr u32 kLongLiteral = 32;  // literals longer than this are copied by the whole warp
 
 // Decode the self-contained element run in[ip .. ie) into o[0 .. on).  Returns false when the run
 // is not clean (bad element, reaches before o, does not end exactly at ie / on).
+//
+// Window-parallel parse: the 32 lanes decode the 32 byte positions base .. base+31 as if each were
+// a tag (loop header of decompress_all_tags!, src/internal.jl:416-439, evaluated for every byte at
+// once); the real chain inside the window is then the set of positions reachable from lane 0,
+// found by pointer doubling on "position + element size" (5 rounds of reduce-or + shuffle).  The
+// element that leaves the window gives the next window's base, so long literals are skipped in one
+// hop.  A warp scan over the chain's lengths gives every element its output offset.
+// Execution: short elements (<= kShortElem bytes) run one per lane, in dependency rounds: an
+// element may go once every output byte it reads lies below the destination of the first
+// unfinished element; long elements are copied by the whole warp when they become the first
+// unfinished one (incremental_copy! / copy_literal!, src/internal.jl:477-527).
+constexpr u32 kShortElem = 16;
+
 __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 ip, const u64 ie,
                                                  u8* __restrict__ o, const u32 on, const u32 lane) {
+    u64 base = ip;
     u32 op = 0;
-    while (ip < ie) {
-        // ---- parse up to 32 elements
-        u32 cnt = 0;
-        u32 my_len = 0, my_dst = 0, my_off = 0;
-        u64 my_src = 0;
-        bool my_copy = false;
-        while (cnt < 32 && ip < ie) {
-            u32 c, tag4;
-            load_tag(in, ip, ie, c, tag4);
-            Element e = decode_tag(c, tag4);
-            ip += 1 + e.extra;
-            if (e.is_copy) {
-                if (ip > ie || e.offset == 0 || e.offset > op || e.len > on - op) return false;
-                if (cnt == lane) { my_len = e.len; my_dst = op; my_off = e.offset; my_copy = true; }
-                cnt++;
-            } else {
-                if (ip > ie || (u64)e.len > ie - ip || e.len > on - op) return false;
-                if (e.len > kLongLiteral) {
-                    warp_copy_literal(o + op, in + ip, e.len, lane);
-                } else {
-                    if (cnt == lane) { my_len = e.len; my_dst = op; my_src = ip; my_copy = false; }
-                    cnt++;
-                }
-                ip += e.len;
-            }
-            op += e.len;
+    while (base < ie) {
+        // ---- decode all 32 byte positions of the window
+        const u64 p = base + lane;
+        const bool inb = p < ie;
+        u32 c = 0, tag4 = 0;
+        if (inb) load_tag(in, p, ie, c, tag4);
+        const Element e = decode_tag(c, tag4);
+        const u64 size = 1ull + e.extra + (e.is_copy ? 0u : e.len);
+        // 32: leaves the window (also when the element ends at or past ie: the run is over)
+        u32 jump = (size >= 32u - lane || p + size >= ie) ? 32u : lane + (u32)size;
+        const bool leaves = jump == 32u;
+        // ---- positions reachable from lane 0 (the chain enters every window at its first byte)
+        u32 R = 1u;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const u32 m = (((R >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u;
+            R |= __reduce_or_sync(kFullMask, m);
+            const u32 j2 = __shfl_sync(kFullMask, jump, jump & 31u);
+            jump = (jump < 32u) ? j2 : 32u;
         }
-        // ---- execute the batch in dependency rounds
-        const u32 active = (cnt == 32) ? kFullMask : ((1u << cnt) - 1);
-        const bool mine = lane < cnt;
-        // highest output byte (exclusive) this element reads; literals read none
-        const u32 need = (mine && my_copy) ? min(my_dst - my_off + my_len, my_dst) : 0;
-        u32 done = ~active;
-        __syncwarp();  // long literals written above are visible to the copies below
-        while (done != kFullMask) {
-            const u32 first = (u32)__ffs((int)~done) - 1;
-            const u32 frontier = __shfl_sync(kFullMask, my_dst, first);
-            const bool ready = mine && !((done >> lane) & 1) && (need <= frontier);
+        const bool mine = (R >> lane) & 1u;
+        // ---- validate the chain's elements (anything odd: let the exact decoder decide)
+        const u64 body = p + 1 + e.extra;  // first byte behind the element header
+        bool bad = mine && (!inb || body > ie || e.len == 0 || e.len > on ||
+                            (!e.is_copy && (u64)e.len > ie - body));
+        const u32 elen = mine ? e.len : 0u;
+        u32 incl = bad ? 0u : elen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (u32)d) incl += t;
+        }
+        const u32 total = __shfl_sync(kFullMask, incl, 31);
+        const u32 dst = op + incl - elen;
+        bad = bad || (mine && e.is_copy && (e.offset == 0 || e.offset > dst));
+        const u32 exitm = __ballot_sync(kFullMask, mine && leaves);
+        if (__any_sync(kFullMask, bad) || exitm == 0 || total > on - op) return false;
+        const u64 nbase = __shfl_sync(kFullMask, p + size, (u32)__ffs((int)exitm) - 1u);
+        // ---- execute
+        const u64 lsrc = body;  // literal bytes start behind the header
+        // highest output byte (exclusive) the element reads; literals read none
+        const u32 need = (mine && e.is_copy) ? (dst - e.offset + min(elen, e.offset)) : 0u;
+        u32 pending = R;
+        while (pending) {
+            const u32 f = (u32)__ffs((int)pending) - 1u;
+            const u32 frontier = __shfl_sync(kFullMask, dst, f);
+            const u32 flen = __shfl_sync(kFullMask, elen, f);
+            if (flen > kShortElem) {
+                const u32 fcopy = __shfl_sync(kFullMask, (u32)e.is_copy, f);
+                if (fcopy) {
+                    const u32 foff = __shfl_sync(kFullMask, e.offset, f);
+                    warp_copy_backref(o, frontier, foff, flen, lane);
+                } else {
+                    const u64 fsrc = __shfl_sync(kFullMask, lsrc, f);
+                    warp_copy_literal(o + frontier, in + fsrc, flen, lane);
+                }
+                __syncwarp();
+                pending &= ~(1u << f);
+                continue;
+            }
+            const bool ready = ((pending >> lane) & 1u) && elen <= kShortElem && need <= frontier;
             if (ready) {
-                u8* d = o + my_dst;
-                if (my_copy) {
-                    const u8* s = o + (my_dst - my_off);
-                    if (my_off >= my_len) {
-                        for (u32 i = 0; i < my_len; i++) d[i] = s[i];
+                u8* d = o + dst;
+                if (e.is_copy) {
+                    const u8* s = o + (dst - e.offset);
+                    if (e.offset >= elen) {
+                        for (u32 i = 0; i < elen; i++) d[i] = s[i];
                     } else {
-                        for (u32 i = 0; i < my_len; i++) d[i] = s[i % my_off];
+                        for (u32 i = 0, k = 0; i < elen; i++) {  // pattern of `offset` bytes repeats
+                            d[i] = s[k];
+                            k = (k + 1 == e.offset) ? 0 : k + 1;
+                        }
                     }
                 } else {
-                    const u8* s = in + my_src;
-                    for (u32 i = 0; i < my_len; i++) d[i] = __ldg(s + i);
+                    const u8* s = in + lsrc;
+                    for (u32 i = 0; i < elen; i++) d[i] = __ldg(s + i);
                 }
             }
             __syncwarp();
-            done |= __ballot_sync(kFullMask, ready);
+            pending &= ~__ballot_sync(kFullMask, ready);
         }
+        op += total;
+        base = nbase;
     }
-    return ip == ie && op == on;
+    return base == ie && op == on;
 }
 
 // in_begin / in_end: the element bytes of the whole stream are in[in_begin .. in_end); the index

@@ -48,6 +48,7 @@ struct DevBuf {
 struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
+    int prefetch_lanes = 8;     // post-copy candidates prefetched into L1 per step
     int l2_chains = 0;          // extra persistent warps per SM with the table in global memory (L2)
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int timing = 1;             // record CUDA events around the dominant kernel
@@ -125,7 +126,9 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompress2SmemBytes));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(kChainPoEntries * 4 + kMaxTableEntries * 2)));
+                            (int)(kMaxTableEntries * 2)));
+    k_init_probe_offsets<<<1, 32>>>();
+    CU(cudaGetLastError());
     CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
@@ -220,14 +223,14 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
         if (grid_b) CU(c.gtables.ensure((size_t)grid_b * kMaxTableEntries * 2));
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
         if (grid_b) CU(cudaEventRecord(c.ev_fork, st));
-        k_compress_chain<true><<<grid_a, 32, kChainPoEntries * 4 + kMaxTableEntries * 2, st>>>(
-            d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr);
+        k_compress_chain<true><<<grid_a, 32, kMaxTableEntries * 2, st>>>(
+            d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, (u32)c.opt.prefetch_lanes);
         launches = 1;
         if (grid_b) {
             CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-            k_compress_chain<false><<<grid_b, 32, kChainPoEntries * 4, c.side>>>(
+            k_compress_chain<false><<<grid_b, 32, 0, c.side>>>(
                 d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
-                (u16*)c.gtables.p);
+                (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes);
             CU(cudaEventRecord(c.ev_join, c.side));
             CU(cudaStreamWaitEvent(st, c.ev_join, 0));
             launches = 2;
@@ -707,6 +710,7 @@ void snappy_b200_set_option(const char* name, int value) {
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
     else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value;
     else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value;
+    else if (!strcmp(name, "prefetch_lanes")) g_ctx.opt.prefetch_lanes = value;
     else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
 }
 
