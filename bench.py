@@ -309,7 +309,7 @@ def run_b200(args):
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if peak else None, "traffic": None,
-        "kernel": "k_compress_fragments" if dominant == "compress" else "k_decode_fragments",
+        "kernel": "k_compress_chain" if dominant == "compress" else "k_decode_fragments",
         "kernel_ms": k_ms, "algorithmic_bytes": alg_c, "peak_source": peak_src,
         "other": {"compress_kernel_ms": kc_ms, "uncompress_kernel_ms": ku_ms,
                   "uncompress_achieved": (alg_u / (ku_ms / 1e3) / 1e9) if ku_ms > 0 else None},

@@ -656,11 +656,12 @@ k_compress_pages(const u8* __restrict__ g_in, const u64* __restrict__ in_off,
 //   offsets[f]   : byte offset of fragment f behind `base` (base = varint header length, or 0)
 //   offsets[nfrag] = base + total
 __global__ void __launch_bounds__(1024)
-k_scan_sizes(const u32* __restrict__ sizes, u32 nfrag, u64 base, u64* __restrict__ offsets) {
+k_scan_sizes(const u32* __restrict__ sizes, u32 nfrag, u64 base, u64* __restrict__ offsets,
+             u64* running = nullptr) {
     __shared__ u64 warp_excl[32];
     __shared__ u64 carry_s;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = base;
+    if (tid == 0) carry_s = base + (running ? *running : 0ull);  // running: total carried from chunk to chunk
     __syncthreads();
     for (u32 blk = 0; blk < nfrag; blk += 1024 * 4) {
         const u32 i0 = blk + tid * 4;
@@ -698,7 +699,10 @@ k_scan_sizes(const u32* __restrict__ sizes, u32 nfrag, u64 base, u64* __restrict
         if (tid == 1023) carry_s = ex;  // thread 1023 ends at carry + this block's total
         __syncthreads();
     }
-    if (tid == 0) offsets[nfrag] = carry_s;
+    if (tid == 0) {
+        offsets[nfrag] = carry_s;
+        if (running) *running = carry_s;
+    }
 }
 
 // K3: concatenate the per-fragment scratch slots into the contiguous stream.  One CTA per

@@ -313,12 +313,15 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(32)
 k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
-                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes) {
+                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes, u32 reserve) {
     extern __shared__ __align__(128) u8 smem[];
     u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) : gtables + (size_t)blockIdx.x * kMaxTableEntries;
     const u32 lane = lane_id();
     const u32 entries = 1u << (32 - shift);
     for (;;) {
+        // slow (global-table) warps leave the last `reserve` fragments to the fast ones, so that
+        // the kernel does not end on a straggler
+        if (reserve && *reinterpret_cast<volatile u32*>(counter) + reserve >= nfrag) break;
         u32 frag = 0;
         if (lane == 0) frag = atomicAdd(counter, 1u);
         frag = __shfl_sync(kFullMask, frag, 0);

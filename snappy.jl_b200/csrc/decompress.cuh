@@ -273,12 +273,15 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
 // in_begin / in_end: the element bytes of the whole stream are in[in_begin .. in_end); the index
 // must start at in_begin and end at in_end.
 __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32)
-k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag,
-                   u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
+k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag, u32 first,
+                   u32 count, u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
                    DecodeResult* __restrict__ res) {
+    // fragments [first, first + count) of the nfrag the index describes (ranges let the host
+    // overlap the device->host copy of finished output with the decoding of the rest)
     const u32 lane = lane_id();
-    const u32 f = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
-    if (f >= nfrag) return;
+    const u32 local = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
+    if (local >= count) return;
+    const u32 f = first + local;
     const u64 ip = frag_off[f];
     const u64 ie = frag_off[f + 1];
     const u64 ob = (u64)f * kBlockSize;

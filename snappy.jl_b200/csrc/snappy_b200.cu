@@ -45,12 +45,17 @@ struct DevBuf {
     }
 };
 
+constexpr int kMaxPipeChunks = 72;                 // 4 GiB / 64 MiB, plus slack
+constexpr size_t kPipeChunkFrags = 4096;           // fragments per pipeline chunk (256 MiB)
+
 struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
-    int prefetch_lanes = 8;     // post-copy candidates prefetched into L1 per step
-    int l2_chains = 0;          // extra persistent warps per SM with the table in global memory (L2)
+    int l2_reserve = 2;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
+    int prefetch_lanes = 0;     // post-copy candidates prefetched into L1 per step
+    int l2_chains = 10;         // extra persistent warps per SM with the table in global memory (L2)
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
+    int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
 };
 
@@ -62,6 +67,8 @@ struct Context {
     // scratch for compress
     DevBuf scratch, frag_sizes, frag_offsets, tail, gtables;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;  // host-buffer API pipeline
+    cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for decode
     DevBuf result, parse_a, parse_b, parse_c, index;
@@ -130,6 +137,13 @@ int ctx_init_locked(int device) {
     k_init_probe_offsets<<<1, 32>>>();
     CU(cudaGetLastError());
     CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxPipeChunks; i++) {
+        CU(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CU(cudaMallocHost(&c.pinned, 4096));
@@ -182,6 +196,41 @@ int parse_varint(const u8* in, size_t n, u32* value, size_t* hdr) {  // src/vari
     return SNAPPY_B200_BAD_VARINT;
 }
 
+// Launch the chain compressor (compress_chain.cuh) over the fragments of d_in[0 .. len): the
+// shared-memory-table warps on `st`, the global-table warps on the side stream (joined back).
+int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* scratch, u32* sizes,
+                         cudaStream_t st, int* launches) {
+    const u32 nfrag = (u32)((len + kBlockSize - 1) / kBlockSize);
+    // padded copy of the last fragment (the chain kernel reads a few bytes past a fragment's end)
+    const u64 tail_start = (u64)(nfrag - 1) * kBlockSize;
+    const size_t tail_len = len - tail_start;
+    CU(c.tail.ensure(kBlockSize + kTailPad + 16));
+    CU(cudaMemcpyAsync(c.tail.p, d_in + tail_start, tail_len, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync((u8*)c.tail.p + tail_len, 0, kTailPad, st));
+    u32* counter = (u32*)((u8*)c.result.p + 64);
+    CU(cudaMemsetAsync(counter, 0, 4, st));
+    const u32 want_a = (u32)c.sm_count * (u32)c.opt.smem_chains;
+    const u32 grid_a = nfrag < want_a ? nfrag : want_a;
+    const u32 reserve = (u32)c.opt.l2_reserve * grid_a;
+    const u32 grid_b = (nfrag > grid_a + reserve) ? (u32)c.sm_count * (u32)c.opt.l2_chains : 0u;
+    if (grid_b) CU(c.gtables.ensure((size_t)grid_b * kMaxTableEntries * 2));
+    if (grid_b) CU(cudaEventRecord(c.ev_fork, st));
+    k_compress_chain<true><<<grid_a, 32, kMaxTableEntries * 2, st>>>(
+        d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
+        (u32)c.opt.prefetch_lanes, 0u);
+    *launches += 1;
+    if (grid_b) {
+        CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+        k_compress_chain<false><<<grid_b, 32, 0, c.side>>>(
+            d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
+            (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes, reserve);
+        CU(cudaEventRecord(c.ev_join, c.side));
+        CU(cudaStreamWaitEvent(st, c.ev_join, 0));
+        *launches += 1;
+    }
+    return SNAPPY_B200_OK;
+}
+
 // Compress the fragments of one shard into d_out + base (elements only) and return the number of
 // bytes behind d_out (base + elements).  d_index (optional): nfrag+1 stream offsets.
 int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 total_len, u8* d_out,
@@ -209,32 +258,9 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
 
     int launches = 0;
     if (c.opt.compress_variant == 0) {
-        // padded copy of the last fragment (the chain kernel reads a few bytes past a fragment's end)
-        const u64 tail_start = (u64)(nfrag - 1) * kBlockSize;
-        const size_t tail_len = shard_len - tail_start;
-        CU(c.tail.ensure(kBlockSize + kTailPad + 16));
-        CU(cudaMemcpyAsync(c.tail.p, d_in + tail_start, tail_len, cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemsetAsync((u8*)c.tail.p + tail_len, 0, kTailPad, st));
-        u32* counter = (u32*)((u8*)c.result.p + 64);
-        CU(cudaMemsetAsync(counter, 0, 4, st));
-        const u32 want_a = (u32)c.sm_count * (u32)c.opt.smem_chains;
-        const u32 grid_a = nfrag < want_a ? nfrag : want_a;
-        const u32 grid_b = (nfrag > grid_a) ? (u32)c.sm_count * (u32)c.opt.l2_chains : 0u;
-        if (grid_b) CU(c.gtables.ensure((size_t)grid_b * kMaxTableEntries * 2));
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
-        if (grid_b) CU(cudaEventRecord(c.ev_fork, st));
-        k_compress_chain<true><<<grid_a, 32, kMaxTableEntries * 2, st>>>(
-            d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, (u32)c.opt.prefetch_lanes);
-        launches = 1;
-        if (grid_b) {
-            CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-            k_compress_chain<false><<<grid_b, 32, 0, c.side>>>(
-                d_in, (u64)shard_len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
-                (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes);
-            CU(cudaEventRecord(c.ev_join, c.side));
-            CU(cudaStreamWaitEvent(st, c.ev_join, 0));
-            launches = 2;
-        }
+        int rc = launch_chain_kernels(c, d_in, shard_len, shift, scratch, sizes, st, &launches);
+        if (rc != SNAPPY_B200_OK) return rc;
     } else {
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
         if (c.opt.compress_variant == 1)
@@ -295,26 +321,45 @@ int decode_exact_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_
 // decode with a device-resident index of nfrag+1 offsets; returns OK, or -1 when the fast path
 // declined (caller falls back)
 int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
-                          const u64* d_index, cudaStream_t st) {
+                          const u64* d_index, cudaStream_t st, u8* host_out = nullptr,
+                          bool* host_copied = nullptr) {
     const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
     if (nfrag == 0) return -1;
     DecodeResult* res = (DecodeResult*)c.result.p;
     CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
-    const u32 grid = (nfrag + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
-    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, (u64)hdr, (u64)n,
-                                                                 d_out, (u64)claimed, res);
+    // host-buffer API: decode in ranges and send each finished range down while the next decodes
+    const bool ranged = host_out && c.opt.host_pipeline && nfrag > kPipeChunkFrags;
+    const u32 step = ranged ? (u32)kPipeChunkFrags : nfrag;
+    int ri = 0;
+    for (u32 f0 = 0; f0 < nfrag; f0 += step, ri++) {
+        const u32 cnt = (nfrag - f0 < step) ? (nfrag - f0) : step;
+        const u32 grid = (cnt + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
+        k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
+                                                                     (u64)n, d_out, (u64)claimed, res);
+        c.last_launches[1] += 1;
+        if (ranged) {
+            const size_t ob = (size_t)f0 * kBlockSize;
+            const size_t ol = ((size_t)claimed - ob < (size_t)cnt * kBlockSize) ? ((size_t)claimed - ob)
+                                                                                 : (size_t)cnt * kBlockSize;
+            CU(cudaEventRecord(c.ev_done[ri], st));
+            CU(cudaStreamWaitEvent(c.s_d2h, c.ev_done[ri], 0));
+            CU(cudaMemcpyAsync(host_out + ob, d_out + ob, ol, cudaMemcpyDeviceToHost, c.s_d2h));
+        }
+    }
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[3], st));
         c.ev_pending[1] = true;
     }
-    c.last_launches[1] += 1;
     CU(cudaGetLastError());
     DecodeResult* h = (DecodeResult*)((u8*)c.pinned + 128);
     CU(cudaMemcpyAsync(h, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ranged) CU(cudaStreamSynchronize(c.s_d2h));
     harvest_timing(c, 1);
-    return h->fallback ? -1 : SNAPPY_B200_OK;
+    if (h->fallback) return -1;
+    if (ranged && host_copied) *host_copied = true;
+    return SNAPPY_B200_OK;
 }
 
 // Segmented speculative parse (parse.cuh): build the side index of an arbitrary stream in
@@ -381,7 +426,8 @@ int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 cla
 }
 
 int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
-                             size_t* out_len, const u64* d_index, cudaStream_t st) {
+                             size_t* out_len, const u64* d_index, cudaStream_t st, u8* host_out = nullptr,
+                             bool* host_copied = nullptr) {
     c.last_launches[1] = 0;
     // the varint header decides the output size (src/Snappy.jl:47)
     u8* hb = (u8*)c.pinned + 256;
@@ -398,14 +444,15 @@ int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, si
     *out_len = claimed;
     if (c.opt.decode_variant != 1) {
         if (d_index) {
-            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, d_index, st);
+            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, d_index, st, host_out, host_copied);
             if (rc >= 0) return rc;
         }
         // arbitrary stream: segmented speculative parse builds the index on the device
         rc = build_index_locked(c, d_in, n, hdr, claimed, st);
         if (rc > 0) return rc;
         if (rc == 0) {
-            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, (const u64*)c.index.p, st);
+            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, (const u64*)c.index.p, st, host_out,
+                                       host_copied);
             if (rc >= 0) return rc;
         }
     }
@@ -459,6 +506,15 @@ void snappy_b200_shutdown(void) {
     cudaSetDevice(c.device);
     if (c.side) cudaStreamDestroy(c.side);
     c.side = nullptr;
+    for (cudaStream_t* sp : {&c.s_h2d, &c.s_d2h, &c.s_comp}) {
+        if (*sp) cudaStreamDestroy(*sp);
+        *sp = nullptr;
+    }
+    for (int i = 0; i < kMaxPipeChunks; i++) {
+        if (c.ev_in[i]) cudaEventDestroy(c.ev_in[i]);
+        if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
+        c.ev_in[i] = c.ev_done[i] = nullptr;
+    }
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
@@ -527,6 +583,69 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
                                     (cudaStream_t)stream);
 }
 
+// Host-buffer compress, pipelined: the input goes up in chunks of
+// kPipeChunkFrags fragments on a copy stream, each chunk is compressed + compacted behind the
+// previous one's bytes as soon as it has landed, and its bytes go back down on a third stream
+// while the next chunk compresses.  Only the chunk totals (8 bytes each) are read by the host.
+int compress_host_pipelined(Context& c, const u8* in, size_t n, u8* out, size_t* out_len) {
+    const size_t need = snappy_b200_max_compressed_length(n);
+    const u32 nfrag = (u32)((n + kBlockSize - 1) / kBlockSize);
+    const int nchunks = (int)((nfrag + kPipeChunkFrags - 1) / kPipeChunkFrags);
+    CU(c.stage_in.ensure(n + 16));
+    CU(c.stage_out.ensure(need + 16));
+    CU(c.scratch.ensure((size_t)nfrag * kSlotStride));
+    CU(c.frag_sizes.ensure((size_t)nfrag * sizeof(u32)));
+    CU(c.frag_offsets.ensure(((size_t)nfrag + 1) * sizeof(u64) + 8));
+    u8* d_in = (u8*)c.stage_in.p;
+    u8* d_out = (u8*)c.stage_out.p;
+    u8* scratch = (u8*)c.scratch.p;
+    u32* sizes = (u32*)c.frag_sizes.p;
+    u64* offs = (u64*)c.frag_offsets.p;
+    u64* running = offs + nfrag + 1;           // device: bytes in the stream so far
+    u64* h_tot = (u64*)((u8*)c.pinned + 2048);  // host: stream length after each chunk
+    const u32 shift = table_shift(n);
+    u8* hdr = (u8*)c.pinned + 64;
+    const int k = encode_varint((u32)n, hdr);   // src/Snappy.jl:26
+    u64* h_k = (u64*)((u8*)c.pinned + 96);
+    *h_k = (u64)k;
+    CU(cudaMemcpyAsync(d_out, hdr, (size_t)k, cudaMemcpyHostToDevice, c.s_comp));
+    CU(cudaMemcpyAsync(running, h_k, 8, cudaMemcpyHostToDevice, c.s_comp));
+    int launches = 0;
+    for (int i = 0; i < nchunks; i++) {
+        const size_t off = (size_t)i * kPipeChunkFrags * kBlockSize;
+        const size_t len = (n - off < kPipeChunkFrags * kBlockSize) ? (n - off) : kPipeChunkFrags * kBlockSize;
+        CU(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c.s_h2d));
+        CU(cudaEventRecord(c.ev_in[i], c.s_h2d));
+    }
+    for (int i = 0; i < nchunks; i++) {
+        const size_t f0 = (size_t)i * kPipeChunkFrags;
+        const size_t off = f0 * kBlockSize;
+        const size_t len = (n - off < kPipeChunkFrags * kBlockSize) ? (n - off) : kPipeChunkFrags * kBlockSize;
+        const u32 nf = (u32)((len + kBlockSize - 1) / kBlockSize);
+        CU(cudaStreamWaitEvent(c.s_comp, c.ev_in[i], 0));
+        int rc = launch_chain_kernels(c, d_in + off, len, shift, scratch + f0 * kSlotStride, sizes + f0,
+                                      c.s_comp, &launches);
+        if (rc != SNAPPY_B200_OK) return rc;
+        k_scan_sizes<<<1, 1024, 0, c.s_comp>>>(sizes + f0, nf, 0, offs + f0, running);
+        k_compact<<<nf, 256, 0, c.s_comp>>>(scratch + f0 * kSlotStride, sizes + f0, offs + f0, d_out);
+        launches += 2;
+        CU(cudaMemcpyAsync(h_tot + i, running, 8, cudaMemcpyDeviceToHost, c.s_comp));
+        CU(cudaEventRecord(c.ev_done[i], c.s_comp));
+    }
+    CU(cudaGetLastError());
+    u64 prev = 0;
+    for (int i = 0; i < nchunks; i++) {
+        CU(cudaEventSynchronize(c.ev_done[i]));
+        const u64 end = h_tot[i];
+        CU(cudaMemcpyAsync(out + prev, d_out + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, c.s_d2h));
+        prev = end;
+    }
+    CU(cudaStreamSynchronize(c.s_d2h));
+    c.last_launches[0] = launches;
+    *out_len = (size_t)prev;
+    return SNAPPY_B200_OK;
+}
+
 int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len) {
     if (!out_len || (!in && n) || !out) return SNAPPY_B200_BAD_ARGUMENT;
     if (n > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;  // src/Snappy.jl:21
@@ -535,9 +654,11 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
     Context& c = g_ctx;
+    if (c.opt.compress_variant == 0 && c.opt.host_pipeline && n > kPipeChunkFrags * kBlockSize)
+        return compress_host_pipelined(c, in, n, out, out_len);
     CU(c.stage_in.ensure(n + 16));
     CU(c.stage_out.ensure(need + 16));
-    cudaStream_t st = 0;
+    cudaStream_t st = c.s_comp;
     if (n) CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
     size_t clen = 0;
     int rc = compress_device_locked(c, (const u8*)c.stage_in.p, n, (u8*)c.stage_out.p, need, &clen,
@@ -561,13 +682,14 @@ int snappy_b200_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t* ou
     Context& c = g_ctx;
     CU(c.stage_in.ensure(n + 16));
     CU(c.stage_out.ensure((size_t)claimed + 16));
-    cudaStream_t st = 0;
+    cudaStream_t st = c.s_comp;
     CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
     size_t olen = 0;
+    bool copied = false;
     rc = uncompress_device_locked(c, (const u8*)c.stage_in.p, n, (u8*)c.stage_out.p, (size_t)claimed,
-                                  &olen, nullptr, st);
+                                  &olen, nullptr, st, out, &copied);
     if (rc != SNAPPY_B200_OK) return rc;
-    if (olen) CU(cudaMemcpyAsync(out, c.stage_out.p, olen, cudaMemcpyDeviceToHost, st));
+    if (olen && !copied) CU(cudaMemcpyAsync(out, c.stage_out.p, olen, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *out_len = olen;
     return SNAPPY_B200_OK;
@@ -608,8 +730,8 @@ int snappy_b200_uncompress_shard_device(const uint8_t* d_in, const uint64_t* d_f
     CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
     const u32 grid = ((u32)nfrag + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
-    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_frag_offsets, (u32)nfrag, h[0],
-                                                                 h[1], d_out, (u64)out_len, res);
+    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_frag_offsets, (u32)nfrag, 0u,
+                                                                 (u32)nfrag, h[0], h[1], d_out, (u64)out_len, res);
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[3], st));
         c.ev_pending[1] = true;
@@ -711,6 +833,8 @@ void snappy_b200_set_option(const char* name, int value) {
     else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value;
     else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value;
     else if (!strcmp(name, "prefetch_lanes")) g_ctx.opt.prefetch_lanes = value;
+    else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
+    else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
     else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
 }
 

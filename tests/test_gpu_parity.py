@@ -257,3 +257,14 @@ def test_full_size_1gib_properties(dev, oracle):
     del back
     back = dev.uncompress_device(stream)  # arbitrary-stream path at full size
     assert torch.equal(back, d)
+
+
+def test_host_api_pipelined_paths(snappy, oracle):
+    """> 256 MiB through the host-buffer C ABI takes the chunk-pipelined H2D / kernel / D2H path
+    (SURVEY.md 8(f)1); the bytes must still be the oracle's, both ways."""
+    from snappy_jl_b200 import synth
+    raw = synth.mix(4096 + 1000, seed=77, tail=4242)
+    got = snappy.compress_np(raw)
+    want = oracle.compress_np(raw)
+    assert got.size == want.size and np.array_equal(got, want)
+    assert np.array_equal(snappy.uncompress_np(want), raw)
