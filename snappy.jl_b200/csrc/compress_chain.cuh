@@ -56,13 +56,14 @@ __global__ void k_init_probe_offsets() {
 
 template <bool kSmemTable>
 struct Chain {
+    static constexpr u32 kSpec = 32u;  // end positions pre-probed per copy
     const u8* F;     // fragment bytes (global, >= 64 readable bytes past n)
     u16* T;          // hash table, position per hash, 0 == empty (global variant)
     u32 Ts;          // shared-space address of the table (shared variant)
     u8* out;         // scratch slot of this fragment
     u32 n, shift, lane, op, nrec, pf_lanes;
     int lim;
-    u32 r_lit, r_cpy;  // lane k parks record k: literal (from | len << 16), copy (offset | M << 16)
+    u32 r_lit, r_cpy;  // lane k parks record k: (lit_from | ip << 16), (cand | M << 16)
 
     __device__ __forceinline__ u32 hash(u32 w) const { return (w * kHashMul) >> shift; }
     __device__ __forceinline__ u32 tget(u32 h) const {
@@ -109,9 +110,13 @@ struct Chain {
     }
 
     __device__ __forceinline__ void flush() {
+        {   // pull the next few KiB of the fragment into L2 ahead of the ip-side loads (32 x 128 B)
+            const u32 ahead = (r_lit >> 16) + kStreamAhead + lane * 128u;  // from this lane's ip
+            if (ahead < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + ahead));
+        }
         const bool mine = lane < nrec;
-        const u32 lf = r_lit & 0xffffu, ll = mine ? (r_lit >> 16) : 0u;
-        const u32 off = r_cpy & 0xffffu, M = mine ? (r_cpy >> 16) : 0u;
+        const u32 lf = r_lit & 0xffffu, ll = mine ? ((r_lit >> 16) - lf) : 0u;
+        const u32 off = (r_lit >> 16) - (r_cpy & 0xffffu), M = mine ? (r_cpy >> 16) : 0u;
         // :271-283 header bytes of the literal (a 60-byte literal already takes the long form)
         const u32 lh = (ll == 0) ? 0u : (ll < 60 ? 1u : ((ll - 1) <= 0xffu ? 2u : ((ll - 1) <= 0xffffu ? 3u : 4u)));
         const u32 sz = lh + ll + copy_bytes(off, M);
@@ -163,11 +168,11 @@ struct Chain {
         nrec = 0;
     }
 
-    __device__ __forceinline__ void keep(u32 from, u32 len, u32 off, u32 M) {
-        // len < 65536 here: the only 65536-byte literal is a whole-fragment remainder (see run())
+    // literal [from, ip) followed by a copy of M bytes from cand (all < 65536)
+    __device__ __forceinline__ void keep(u32 from, u32 ip, u32 cand, u32 M) {
         if (lane == nrec) {
-            r_lit = from | (len << 16);
-            r_cpy = off | (M << 16);
+            r_lit = from | (ip << 16);
+            r_cpy = cand | (M << 16);
         }
         if (++nrec == 32) flush();
     }
@@ -207,10 +212,14 @@ struct Chain {
 
     // ---- the fragment --------------------------------------------------------------------------
     __device__ __forceinline__ void run() {
+        // keep these in registers: without the barrier ptxas re-derives them (64-bit min, S2R,
+        // shared-window base) inside the copy loop, ~20 instructions per step
+        asm volatile("" : "+r"(n), "+r"(Ts), "+r"(shift));
         op = 0;
         nrec = 0;
         r_lit = r_cpy = 0;
         lim = (int)n - 16;  // ip_limit, :131
+        asm volatile("" : "+r"(lim));
         u32 ip = 0, lit_from = 0;
         if (n >= kInputMargin) {
             bool finished = false;
@@ -240,12 +249,10 @@ struct Chain {
                     const u32 Wme = __funnelshift_r(elo, ehi, (u32)ea << 3);                 // bytes [e-1, e+3)
                     const u32 We = __funnelshift_rc(elo, ehi, (((u32)ea & 3u) << 3) + 8u);  // bytes [e, e+4)
                     const u32 He = hash(We), Hme = hash(Wme);
-                    const u32 te = tget(He);
+                    // global-table warps pre-probe only the kSpec shortest copies (M = 4 .. 3+kSpec, the
+                    // bulk of all copies): 32-lane gathers from L2 are what slows them down
+                    const u32 te = (kSpec == 32 || lane < kSpec) ? tget(He) : 0u;
                     const u32 ce = (Hme == He) ? (e - 1) : te;  // :233 is visible to :234
-                    if (lane < pf_lanes)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(F + ce));
-                    if (lane == 31 && ip + kStreamAhead < n)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(F + ip + kStreamAhead));
                     u32 M = neq ? (u32)__ffs((int)neq) - 1u : 32u;
                     if (!verified && M < 4) break;  // :238 no match at ip: back to scanning from ip+1
                     if (M == 32) {                  // long match: keep comparing, 32 bytes per round
@@ -259,12 +266,12 @@ struct Chain {
                         }
                     }
                     if (ip + M > n) M = n - ip;  // find_match_length stops at the fragment end (:344-387)
-                    keep(lit_from, ip - lit_from, ip - cand, M);  // :200,:217
+                    keep(lit_from, ip, cand, M);  // :200,:217
                     ip += M;
                     lit_from = ip;
                     if ((int)ip >= lim) { finished = true; break; }  // :222
                     u32 c2;
-                    if (M < 36) {
+                    if (M < 4 + kSpec) {
                         const u32 owner = M - 4;
                         c2 = __shfl_sync(kFullMask, ce, owner);
                         if (lane == owner) {
@@ -306,16 +313,21 @@ struct Chain {
     }
 };
 
-// Persistent warps: one CTA = one warp; fragments are pulled from *counter.
+// Persistent warps; fragments are pulled from *counter.  One CTA per SM with `blockDim.x / 32` warps:
+// 7 shared-memory tables of 32 KiB fit one CTA (7 x 32 KiB + the 1 KiB the system reserves per CTA
+// <= 227 KiB) where seven 1-warp CTAs would not.  Warps never synchronise with each other.
 //   tail_copy : padded copy of the shard's LAST fragment (so reads may run past its end)
-//   gtables   : kSmemTable == false: one 32 KiB table per CTA in global memory
+//   gtables   : kSmemTable == false: one 32 KiB table per warp in global memory
 template <bool kSmemTable>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(512)
 k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
                  u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes, u32 reserve) {
     extern __shared__ __align__(128) u8 smem[];
-    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) : gtables + (size_t)blockIdx.x * kMaxTableEntries;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * kMaxTableEntries
+                        : gtables + (size_t)gwarp * kMaxTableEntries;
     const u32 lane = lane_id();
     const u32 entries = 1u << (32 - shift);
     for (;;) {

@@ -179,20 +179,57 @@ constexpr u32 kDecodeWarpsPerCta = 4;
 // unfinished one (incremental_copy! / copy_literal!, src/internal.jl:477-527).
 constexpr u32 kShortElem = 16;
 
+// branch-free form of decode_tag for the window parse (same fields; CHAR_TABLE / WORDMASK of
+// src/internal.jl:47-85 evaluated arithmetically)
+__device__ __forceinline__ void decode_tag_fast(u32 c, u32 tag4, u32& len, u32& offset, u32& extra,
+                                                bool& is_copy) {
+    const u32 kind = c & 3u, hi = c >> 2;
+    extra = (kind == 0) ? (hi >= 60 ? hi - 59 : 0u) : (kind == 3 ? 4u : kind);
+    const u32 mask = (extra >= 4) ? 0xffffffffu : ((1u << (8u * extra)) - 1u);
+    const u32 v = tag4 & mask;
+    is_copy = kind != 0;
+    len = (kind == 0) ? (hi >= 60 ? 1u + v : hi + 1u) : (kind == 1 ? 4u + (hi & 7u) : hi + 1u);
+    offset = (kind == 1) ? (((c >> 5) << 8) | v) : v;
+}
+
 __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 ip, const u64 ie,
                                                  u8* __restrict__ o, const u32 on, const u32 lane) {
-    u64 base = ip;
-    u32 op = 0;
-    while (base < ie) {
+    if (ie - ip > 0xfffffff0ull) return false;
+    const u8* __restrict__ src = in + ip;   // all positions below are relative to the run start
+    const u32 nin = (u32)(ie - ip);
+    u32 base = 0, op = 0;
+    while (base < nin) {
         // ---- decode all 32 byte positions of the window
-        const u64 p = base + lane;
-        const bool inb = p < ie;
+        const u32 p = base + lane;
+        const bool inb = p < nin;
+        const u32 rem = inb ? nin - p : 1u;  // bytes from p to the end of the run (>= 1)
         u32 c = 0, tag4 = 0;
-        if (inb) load_tag(in, p, ie, c, tag4);
-        const Element e = decode_tag(c, tag4);
-        const u64 size = 1ull + e.extra + (e.is_copy ? 0u : e.len);
-        // 32: leaves the window (also when the element ends at or past ie: the run is over)
-        u32 jump = (size >= 32u - lane || p + size >= ie) ? 32u : lane + (u32)size;
+        if (inb) {
+            if (rem >= 12) {
+                // three aligned words cover the 5 bytes at any misalignment of the address
+                const uintptr_t pa = reinterpret_cast<uintptr_t>(src + p);
+                const u32* w = reinterpret_cast<const u32*>(pa & ~(uintptr_t)3);
+                const u32 sh = (u32)pa << 3;
+                const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                const u32 lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                c = lo & 0xffu;
+                tag4 = __funnelshift_r(lo, hi, 8);
+            } else {
+                c = src[p];
+#pragma unroll
+                for (u32 k = 0; k < 4; k++)
+                    if (1 + k < rem) tag4 |= (u32)src[p + 1 + k] << (8 * k);  // zero-padded, :426-430
+            }
+        }
+        u32 elen0, eoff, extra;
+        bool is_copy;
+        decode_tag_fast(c, tag4, elen0, eoff, extra, is_copy);
+        // element size, saturated to "one past the end of the run" when it does not fit
+        const u32 hdr = 1u + extra;
+        const bool fits = hdr <= rem && (is_copy || elen0 <= rem - hdr);
+        const u32 size = fits ? hdr + (is_copy ? 0u : elen0) : rem + 1u;
+        // 32: leaves the window (also when the element ends at or past the end: the run is over)
+        u32 jump = (size >= 32u - lane || size >= rem) ? 32u : lane + size;
         const bool leaves = jump == 32u;
         // ---- positions reachable from lane 0 (the chain enters every window at its first byte)
         u32 R = 1u;
@@ -205,10 +242,8 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
         }
         const bool mine = (R >> lane) & 1u;
         // ---- validate the chain's elements (anything odd: let the exact decoder decide)
-        const u64 body = p + 1 + e.extra;  // first byte behind the element header
-        bool bad = mine && (!inb || body > ie || e.len == 0 || e.len > on ||
-                            (!e.is_copy && (u64)e.len > ie - body));
-        const u32 elen = mine ? e.len : 0u;
+        bool bad = mine && (!inb || !fits || elen0 == 0 || elen0 > on);
+        const u32 elen = mine ? elen0 : 0u;
         u32 incl = bad ? 0u : elen;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -217,28 +252,24 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
         }
         const u32 total = __shfl_sync(kFullMask, incl, 31);
         const u32 dst = op + incl - elen;
-        bad = bad || (mine && e.is_copy && (e.offset == 0 || e.offset > dst));
+        bad = bad || (mine && is_copy && (eoff == 0 || eoff > dst));
         const u32 exitm = __ballot_sync(kFullMask, mine && leaves);
         if (__any_sync(kFullMask, bad) || exitm == 0 || total > on - op) return false;
-        const u64 nbase = __shfl_sync(kFullMask, p + size, (u32)__ffs((int)exitm) - 1u);
+        const u32 nbase = __shfl_sync(kFullMask, p + size, (u32)__ffs((int)exitm) - 1u);
         // ---- execute
-        const u64 lsrc = body;  // literal bytes start behind the header
+        const u32 lsrc = p + hdr;  // literal bytes start behind the header
         // highest output byte (exclusive) the element reads; literals read none
-        const u32 need = (mine && e.is_copy) ? (dst - e.offset + min(elen, e.offset)) : 0u;
+        const u32 need = (mine && is_copy) ? (dst - eoff + min(elen, eoff)) : 0u;
         u32 pending = R;
         while (pending) {
             const u32 f = (u32)__ffs((int)pending) - 1u;
             const u32 frontier = __shfl_sync(kFullMask, dst, f);
             const u32 flen = __shfl_sync(kFullMask, elen, f);
             if (flen > kShortElem) {
-                const u32 fcopy = __shfl_sync(kFullMask, (u32)e.is_copy, f);
-                if (fcopy) {
-                    const u32 foff = __shfl_sync(kFullMask, e.offset, f);
-                    warp_copy_backref(o, frontier, foff, flen, lane);
-                } else {
-                    const u64 fsrc = __shfl_sync(kFullMask, lsrc, f);
-                    warp_copy_literal(o + frontier, in + fsrc, flen, lane);
-                }
+                const u32 fcopy = __shfl_sync(kFullMask, (u32)is_copy, f);
+                const u32 fx = __shfl_sync(kFullMask, is_copy ? eoff : lsrc, f);
+                if (fcopy) warp_copy_backref(o, frontier, fx, flen, lane);
+                else warp_copy_literal(o + frontier, src + fx, flen, lane);
                 __syncwarp();
                 pending &= ~(1u << f);
                 continue;
@@ -246,18 +277,18 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
             const bool ready = ((pending >> lane) & 1u) && elen <= kShortElem && need <= frontier;
             if (ready) {
                 u8* d = o + dst;
-                if (e.is_copy) {
-                    const u8* s = o + (dst - e.offset);
-                    if (e.offset >= elen) {
+                if (is_copy) {
+                    const u8* s = o + (dst - eoff);
+                    if (eoff >= elen) {
                         for (u32 i = 0; i < elen; i++) d[i] = s[i];
                     } else {
                         for (u32 i = 0, k = 0; i < elen; i++) {  // pattern of `offset` bytes repeats
                             d[i] = s[k];
-                            k = (k + 1 == e.offset) ? 0 : k + 1;
+                            k = (k + 1 == eoff) ? 0 : k + 1;
                         }
                     }
                 } else {
-                    const u8* s = in + lsrc;
+                    const u8* s = src + lsrc;
                     for (u32 i = 0; i < elen; i++) d[i] = __ldg(s + i);
                 }
             }
@@ -267,12 +298,13 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
         op += total;
         base = nbase;
     }
-    return base == ie && op == on;
+    return base == nin && op == on;
 }
 
 // in_begin / in_end: the element bytes of the whole stream are in[in_begin .. in_end); the index
 // must start at in_begin and end at in_end.
-__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, kMinBlocks)
 k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag, u32 first,
                    u32 count, u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
                    DecodeResult* __restrict__ res) {

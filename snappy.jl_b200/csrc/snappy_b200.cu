@@ -53,8 +53,9 @@ struct Options {
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
     int l2_reserve = 2;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
     int prefetch_lanes = 0;     // post-copy candidates prefetched into L1 per step
-    int l2_chains = 10;         // extra persistent warps per SM with the table in global memory (L2)
+    int l2_chains = 14;         // extra persistent warps per SM with the table in global memory (L2)
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
+    int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
 };
@@ -133,7 +134,7 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompress2SmemBytes));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(kMaxTableEntries * 2)));
+                            (int)(7 * kMaxTableEntries * 2)));
     k_init_probe_offsets<<<1, 32>>>();
     CU(cudaGetLastError());
     CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
@@ -209,19 +210,22 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     CU(cudaMemsetAsync((u8*)c.tail.p + tail_len, 0, kTailPad, st));
     u32* counter = (u32*)((u8*)c.result.p + 64);
     CU(cudaMemsetAsync(counter, 0, 4, st));
-    const u32 want_a = (u32)c.sm_count * (u32)c.opt.smem_chains;
-    const u32 grid_a = nfrag < want_a ? nfrag : want_a;
-    const u32 reserve = (u32)c.opt.l2_reserve * grid_a;
-    const u32 grid_b = (nfrag > grid_a + reserve) ? (u32)c.sm_count * (u32)c.opt.l2_chains : 0u;
-    if (grid_b) CU(c.gtables.ensure((size_t)grid_b * kMaxTableEntries * 2));
-    if (grid_b) CU(cudaEventRecord(c.ev_fork, st));
-    k_compress_chain<true><<<grid_a, 32, kMaxTableEntries * 2, st>>>(
+    // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
+    const u32 wa = (u32)c.opt.smem_chains, wb = (u32)c.opt.l2_chains;
+    u32 ctas_a = (nfrag + wa - 1) / wa;
+    if (ctas_a > (u32)c.sm_count) ctas_a = (u32)c.sm_count;
+    const u32 warps_a = ctas_a * wa;
+    const u32 reserve = (u32)c.opt.l2_reserve * warps_a;
+    const u32 ctas_b = (wb && nfrag > warps_a + reserve) ? (u32)c.sm_count : 0u;
+    if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * kMaxTableEntries * 2));
+    if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
+    k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
         d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
         (u32)c.opt.prefetch_lanes, 0u);
     *launches += 1;
-    if (grid_b) {
+    if (ctas_b) {
         CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-        k_compress_chain<false><<<grid_b, 32, 0, c.side>>>(
+        k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
             d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
             (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes, reserve);
         CU(cudaEventRecord(c.ev_join, c.side));
@@ -335,8 +339,15 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
     for (u32 f0 = 0; f0 < nfrag; f0 += step, ri++) {
         const u32 cnt = (nfrag - f0 < step) ? (nfrag - f0) : step;
         const u32 grid = (cnt + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
-        k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
-                                                                     (u64)n, d_out, (u64)claimed, res);
+        if (c.opt.decode_occupancy == 12)
+            k_decode_fragments<12><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
+                                                                             (u64)n, d_out, (u64)claimed, res);
+        else if (c.opt.decode_occupancy == 10)
+            k_decode_fragments<10><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
+                                                                             (u64)n, d_out, (u64)claimed, res);
+        else
+            k_decode_fragments<8><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
+                                                                            (u64)n, d_out, (u64)claimed, res);
         c.last_launches[1] += 1;
         if (ranged) {
             const size_t ob = (size_t)f0 * kBlockSize;
@@ -730,7 +741,7 @@ int snappy_b200_uncompress_shard_device(const uint8_t* d_in, const uint64_t* d_f
     CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
     const u32 grid = ((u32)nfrag + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
-    k_decode_fragments<<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_frag_offsets, (u32)nfrag, 0u,
+    k_decode_fragments<8><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_frag_offsets, (u32)nfrag, 0u,
                                                                  (u32)nfrag, h[0], h[1], d_out, (u64)out_len, res);
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[3], st));
@@ -830,11 +841,12 @@ void snappy_b200_set_option(const char* name, int value) {
     if (!name) return;
     if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
-    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value;
-    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value;
+    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 1 ? 1 : (value > 7 ? 7 : value);
+    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 16 ? 16 : value);
     else if (!strcmp(name, "prefetch_lanes")) g_ctx.opt.prefetch_lanes = value;
     else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
     else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
+    else if (!strcmp(name, "decode_occupancy")) g_ctx.opt.decode_occupancy = value;
     else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
 }
 

@@ -11,10 +11,13 @@ raw = synth.mix(nfrag, seed=2026)
 d = torch.from_numpy(raw).cuda()
 stream, index = device.compress_device(d, want_index=True)
 print("compressed", raw.size, "->", stream.numel())
-for name, kw in (("indexed", dict(index=index)), ("noindex", dict())):
+for occ in (8, 10, 12):
+  device.set_option("decode_occupancy", occ)
+  print("occupancy", occ)
+  for name, kw in (("indexed", dict(index=index)),):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         back = device.uncompress_device(stream, claimed=raw.size, **kw)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        print(name, rep, "%.2f ms" % (dt * 1e3), "launches", device.last_launch_count(1),
+        print(' ',name, rep, "%.2f ms" % (dt * 1e3), "launches", device.last_launch_count(1),
               "kernel_ms %.2f" % device.last_kernel_ms(1), "ok", bool(torch.equal(back, d)))
