@@ -125,6 +125,19 @@ int snappy_b200_compress_shard_device(const uint8_t *d_shard, size_t shard_len, 
 int snappy_b200_uncompress_shard_device(const uint8_t *d_in, const uint64_t *d_frag_offsets,
                                         size_t nfrag, uint8_t *d_out, size_t out_len, void *stream);
 
+/* Batched forms of the two shard calls: `count` shards (runs of whole fragments, possibly of
+ * different streams) go through ONE kernel pass, which is what keeps the GPU full when a rank
+ * holds many small shards (8 streams x 1/8 each).  The arrays are HOST arrays of `count` entries
+ * whose pointer members are DEVICE pointers; d_frag_sizes (and its entries) may be NULL. */
+int snappy_b200_compress_shards_device(const uint8_t *const *d_shards, const size_t *shard_lens,
+                                       const uint64_t *total_lens, size_t count,
+                                       uint8_t *const *d_outs, const size_t *out_caps,
+                                       size_t *out_lens, uint32_t *const *d_frag_sizes, void *stream);
+int snappy_b200_uncompress_shards_device(const uint8_t *const *d_ins,
+                                         const uint64_t *const *d_frag_offsets,
+                                         const size_t *out_lens, size_t count,
+                                         uint8_t *const *d_outs, void *stream);
+
 /* varint.jl:46-69 / :12-37 on the host (the stream header). Returns bytes written (1..5). */
 int snappy_b200_encode_header(uint32_t value, uint8_t out[5]);
 int snappy_b200_parse_header(const uint8_t *in, size_t n, uint32_t *value, size_t *header_len);

@@ -45,6 +45,8 @@ SIGNATURES = {
     "snappy_b200_compress_shard_device": (ctypes.c_int,
                                           [_vp, _sz, ctypes.c_uint64, _vp, _sz, _szp, _vp, _vp]),
     "snappy_b200_uncompress_shard_device": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "snappy_b200_compress_shards_device": (ctypes.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "snappy_b200_uncompress_shards_device": (ctypes.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "snappy_b200_encode_header": (ctypes.c_int, [ctypes.c_uint32, _vp]),
     "snappy_b200_parse_header": (ctypes.c_int, [_vp, _sz, ctypes.POINTER(ctypes.c_uint32), _szp]),
     "snappy_b200_find_match_length": (_sz, [_vp, _sz, _sz, _sz]),

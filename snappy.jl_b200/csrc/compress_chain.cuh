@@ -313,6 +313,15 @@ struct Chain {
     }
 };
 
+// One entry per shard for the batched shard API: fragments [frag_begin, frag_begin + nfrag) of the
+// launch belong to this shard.
+struct ShardDesc {
+    const u8* ptr;   // first byte of the shard
+    const u8* tail;  // padded copy of its last fragment
+    u64 len;
+    u32 frag_begin, nfrag, shift, pad_;
+};
+
 // Persistent warps; fragments are pulled from *counter.  One CTA per SM with `blockDim.x / 32` warps:
 // 7 shared-memory tables of 32 KiB fit one CTA (7 x 32 KiB + the 1 KiB the system reserves per CTA
 // <= 227 KiB) where seven 1-warp CTAs would not.  Warps never synchronise with each other.
@@ -322,14 +331,14 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(512)
 k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
-                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes, u32 reserve) {
+                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes, u32 reserve,
+                 const ShardDesc* __restrict__ descs, u32 ndesc) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
     const u32 gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * kMaxTableEntries
                         : gtables + (size_t)gwarp * kMaxTableEntries;
     const u32 lane = lane_id();
-    const u32 entries = 1u << (32 - shift);
     for (;;) {
         // slow (global-table) warps leave the last `reserve` fragments to the fast ones, so that
         // the kernel does not end on a straggler
@@ -338,18 +347,34 @@ k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shif
         if (lane == 0) frag = atomicAdd(counter, 1u);
         frag = __shfl_sync(kFullMask, frag, 0);
         if (frag >= nfrag) break;
-        const u64 start = (u64)frag * kBlockSize;
-        const u32 n = (u32)((shard_len - start < kBlockSize) ? (shard_len - start) : kBlockSize);
+        // which shard (batched API: several shards share one launch), else the single shard
+        const u8* sbase = g_in;
+        const u8* stail = tail_copy;
+        u64 slen = shard_len;
+        u32 local = frag, lastf = nfrag - 1, fshift = shift;
+        if (descs) {
+            u32 k = 0;
+            while (k + 1 < ndesc && descs[k + 1].frag_begin <= frag) k++;
+            sbase = descs[k].ptr;
+            stail = descs[k].tail;
+            slen = descs[k].len;
+            local = frag - descs[k].frag_begin;
+            lastf = descs[k].nfrag - 1;
+            fshift = descs[k].shift;
+        }
+        const u64 start = (u64)local * kBlockSize;
+        const u32 n = (u32)((slen - start < kBlockSize) ? (slen - start) : kBlockSize);
+        const u32 entries = 1u << (32 - fshift);
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         Chain<kSmemTable> ch;
-        ch.F = (frag == nfrag - 1) ? tail_copy : g_in + start;
+        ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;
         ch.Ts = kSmemTable ? smem_u32(T) : 0u;
         ch.out = scratch + (u64)frag * kSlotStride;
         ch.n = n;
-        ch.shift = shift;
+        ch.shift = fshift;
         ch.lane = lane;
         ch.pf_lanes = pf_lanes;
         ch.run();

@@ -303,17 +303,40 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
 
 // in_begin / in_end: the element bytes of the whole stream are in[in_begin .. in_end); the index
 // must start at in_begin and end at in_end.
+// One entry per shard for the batched shard API (fragments [frag_begin, frag_begin + nfrag) of the
+// launch): element bytes of fragment i are in[frag_off[i] .. frag_off[i+1]), output at out + i*65536.
+struct DecodeDesc {
+    const u8* in;
+    const u64* frag_off;
+    u8* out;
+    u64 out_len;
+    u32 frag_begin, nfrag;
+};
+
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, kMinBlocks)
 k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag, u32 first,
                    u32 count, u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
-                   DecodeResult* __restrict__ res) {
+                   DecodeResult* __restrict__ res, const DecodeDesc* __restrict__ descs = nullptr,
+                   u32 ndesc = 0) {
     // fragments [first, first + count) of the nfrag the index describes (ranges let the host
     // overlap the device->host copy of finished output with the decoding of the rest)
     const u32 lane = lane_id();
     const u32 local = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
     if (local >= count) return;
-    const u32 f = first + local;
+    u32 f = first + local;
+    if (descs) {  // batched shards: find the shard, take its own arrays and bounds
+        u32 k = 0;
+        while (k + 1 < ndesc && descs[k + 1].frag_begin <= f) k++;
+        in = descs[k].in;
+        frag_off = descs[k].frag_off;
+        out = descs[k].out;
+        out_len = descs[k].out_len;
+        nfrag = descs[k].nfrag;
+        f -= descs[k].frag_begin;
+        in_begin = frag_off[0];
+        in_end = frag_off[nfrag];
+    }
     const u64 ip = frag_off[f];
     const u64 ie = frag_off[f + 1];
     const u64 ob = (u64)f * kBlockSize;

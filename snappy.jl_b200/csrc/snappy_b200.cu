@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "compress.cuh"
 #include "compress_chain.cuh"
@@ -66,7 +67,7 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     // scratch for compress
-    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables;
+    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;  // host-buffer API pipeline
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
@@ -199,15 +200,31 @@ int parse_varint(const u8* in, size_t n, u32* value, size_t* hdr) {  // src/vari
 
 // Launch the chain compressor (compress_chain.cuh) over the fragments of d_in[0 .. len): the
 // shared-memory-table warps on `st`, the global-table warps on the side stream (joined back).
-int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* scratch, u32* sizes,
-                         cudaStream_t st, int* launches) {
+constexpr size_t kTailSlot = kBlockSize + kTailPad + 256;
+
+// padded copy of a shard's last fragment into tail slot `slot` (the chain kernel reads a few bytes
+// past a fragment's end)
+int stage_tail(Context& c, const u8* d_in, size_t len, size_t slot, cudaStream_t st) {
     const u32 nfrag = (u32)((len + kBlockSize - 1) / kBlockSize);
-    // padded copy of the last fragment (the chain kernel reads a few bytes past a fragment's end)
     const u64 tail_start = (u64)(nfrag - 1) * kBlockSize;
     const size_t tail_len = len - tail_start;
-    CU(c.tail.ensure(kBlockSize + kTailPad + 16));
-    CU(cudaMemcpyAsync(c.tail.p, d_in + tail_start, tail_len, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemsetAsync((u8*)c.tail.p + tail_len, 0, kTailPad, st));
+    u8* t = (u8*)c.tail.p + slot * kTailSlot;
+    CU(cudaMemcpyAsync(t, d_in + tail_start, tail_len, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(t + tail_len, 0, kTailPad, st));
+    return SNAPPY_B200_OK;
+}
+
+// descs == nullptr: the fragments of d_in[0 .. len); else `nfrag_total` fragments described by the
+// device array descs[ndesc] (tails already staged).
+int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* scratch, u32* sizes,
+                         cudaStream_t st, int* launches, const ShardDesc* descs = nullptr, u32 ndesc = 0,
+                         u32 nfrag_total = 0) {
+    const u32 nfrag = descs ? nfrag_total : (u32)((len + kBlockSize - 1) / kBlockSize);
+    if (!descs) {
+        CU(c.tail.ensure(kTailSlot));
+        int rc = stage_tail(c, d_in, len, 0, st);
+        if (rc != SNAPPY_B200_OK) return rc;
+    }
     u32* counter = (u32*)((u8*)c.result.p + 64);
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
@@ -221,13 +238,13 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
     k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
         d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
-        (u32)c.opt.prefetch_lanes, 0u);
+        (u32)c.opt.prefetch_lanes, 0u, descs, ndesc);
     *launches += 1;
     if (ctas_b) {
         CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
         k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
             d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
-            (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes, reserve);
+            (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes, reserve, descs, ndesc);
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -529,7 +546,7 @@ void snappy_b200_shutdown(void) {
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
-    for (DevBuf* b : {&c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
+    for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
                       &c.parse_c, &c.index, &c.stage_in, &c.stage_out})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
@@ -754,6 +771,137 @@ int snappy_b200_uncompress_shard_device(const uint8_t* d_in, const uint64_t* d_f
     CU(cudaStreamSynchronize(st));
     harvest_timing(c, 1);
     // a shard has no stream-order context for exact error attribution
+    return hr->fallback ? SNAPPY_B200_INVALID_INPUT : SNAPPY_B200_OK;
+}
+
+int snappy_b200_compress_shards_device(const uint8_t* const* d_shards, const size_t* shard_lens,
+                                       const uint64_t* total_lens, size_t count, uint8_t* const* d_outs,
+                                       const size_t* out_caps, size_t* out_lens,
+                                       uint32_t* const* d_frag_sizes, void* stream) {
+    if (count == 0) return SNAPPY_B200_OK;
+    if (!d_shards || !shard_lens || !total_lens || !d_outs || !out_caps || !out_lens || count > 4096)
+        return SNAPPY_B200_BAD_ARGUMENT;
+    std::vector<ShardDesc> descs;
+    std::vector<size_t> owner;  // descs[i] describes shard owner[i] (empty shards have no desc)
+    u64 nfrag_total = 0;
+    for (size_t k = 0; k < count; k++) {
+        out_lens[k] = 0;
+        if (total_lens[k] > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;
+        if (shard_lens[k] > total_lens[k] || (!d_shards[k] && shard_lens[k]) || !d_outs[k])
+            return SNAPPY_B200_BAD_ARGUMENT;
+        if (out_caps[k] < snappy_b200_max_compressed_length(shard_lens[k])) return SNAPPY_B200_BUFFER_TOO_SMALL;
+        const u32 nf = (u32)((shard_lens[k] + kBlockSize - 1) / kBlockSize);
+        if (nf == 0) continue;
+        ShardDesc d;
+        d.ptr = d_shards[k];
+        d.tail = nullptr;
+        d.len = shard_lens[k];
+        d.frag_begin = (u32)nfrag_total;
+        d.nfrag = nf;
+        d.shift = table_shift(total_lens[k]);
+        d.pad_ = 0;
+        descs.push_back(d);
+        owner.push_back(k);
+        nfrag_total += nf;
+    }
+    if (descs.empty()) return SNAPPY_B200_OK;
+    if (nfrag_total > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    const u32 nd = (u32)descs.size();
+    CU(c.tail.ensure(kTailSlot * nd));
+    CU(c.scratch.ensure((size_t)nfrag_total * kSlotStride));
+    CU(c.frag_sizes.ensure((size_t)nfrag_total * sizeof(u32)));
+    CU(c.frag_offsets.ensure(((size_t)nfrag_total + nd + 1) * sizeof(u64)));
+    CU(c.descs.ensure(sizeof(ShardDesc) * nd));
+    for (u32 i = 0; i < nd; i++) {
+        descs[i].tail = (const u8*)c.tail.p + (size_t)i * kTailSlot;
+        int rc = stage_tail(c, descs[i].ptr, (size_t)descs[i].len, i, st);
+        if (rc != SNAPPY_B200_OK) return rc;
+    }
+    CU(cudaMemcpyAsync(c.descs.p, descs.data(), sizeof(ShardDesc) * nd, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // descs.data() is pageable host memory
+    u8* scratch = (u8*)c.scratch.p;
+    u32* sizes = (u32*)c.frag_sizes.p;
+    u64* offs = (u64*)c.frag_offsets.p;
+    int launches = 0;
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
+    int rc = launch_chain_kernels(c, nullptr, 0, 0, scratch, sizes, st, &launches, (const ShardDesc*)c.descs.p,
+                                  nd, (u32)nfrag_total);
+    if (rc != SNAPPY_B200_OK) return rc;
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[1], st));
+        c.ev_pending[0] = true;
+    }
+    u64* h = (u64*)((u8*)c.pinned + 2048);
+    if (nd > 200) return SNAPPY_B200_BAD_ARGUMENT;  // pinned readback area
+    for (u32 i = 0; i < nd; i++) {
+        const u32 fb = descs[i].frag_begin, nf = descs[i].nfrag;
+        u64* o = offs + fb + i;  // nf + 1 entries per shard
+        k_scan_sizes<<<1, 1024, 0, st>>>(sizes + fb, nf, 0, o);
+        k_compact<<<nf, 256, 0, st>>>(scratch + (size_t)fb * kSlotStride, sizes + fb, o, d_outs[owner[i]]);
+        launches += 2;
+        CU(cudaMemcpyAsync(h + i, o + nf, 8, cudaMemcpyDeviceToHost, st));
+        if (d_frag_sizes && d_frag_sizes[owner[i]])
+            CU(cudaMemcpyAsync(d_frag_sizes[owner[i]], sizes + fb, (size_t)nf * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 0);
+    c.last_launches[0] = launches;
+    for (u32 i = 0; i < nd; i++) out_lens[owner[i]] = (size_t)h[i];
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_uncompress_shards_device(const uint8_t* const* d_ins, const uint64_t* const* d_frag_offsets,
+                                         const size_t* out_lens, size_t count, uint8_t* const* d_outs,
+                                         void* stream) {
+    if (count == 0) return SNAPPY_B200_OK;
+    if (!d_ins || !d_frag_offsets || !out_lens || !d_outs || count > 4096) return SNAPPY_B200_BAD_ARGUMENT;
+    std::vector<DecodeDesc> descs;
+    u64 nfrag_total = 0;
+    for (size_t k = 0; k < count; k++) {
+        const u32 nf = (u32)((out_lens[k] + kBlockSize - 1) / kBlockSize);
+        if (nf == 0) continue;
+        if (!d_ins[k] || !d_frag_offsets[k] || !d_outs[k]) return SNAPPY_B200_BAD_ARGUMENT;
+        DecodeDesc d;
+        d.in = d_ins[k];
+        d.frag_off = d_frag_offsets[k];
+        d.out = d_outs[k];
+        d.out_len = out_lens[k];
+        d.frag_begin = (u32)nfrag_total;
+        d.nfrag = nf;
+        descs.push_back(d);
+        nfrag_total += nf;
+    }
+    if (descs.empty()) return SNAPPY_B200_OK;
+    if (nfrag_total > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
+    Locked L;
+    if (L.rc != SNAPPY_B200_OK) return L.rc;
+    Context& c = g_ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    const u32 nd = (u32)descs.size();
+    CU(c.descs.ensure(sizeof(DecodeDesc) * nd));
+    CU(cudaMemcpyAsync(c.descs.p, descs.data(), sizeof(DecodeDesc) * nd, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    const u32 grid = ((u32)nfrag_total + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
+    k_decode_fragments<12><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(nullptr, nullptr, 0u, 0u, (u32)nfrag_total, 0, 0,
+                                                                     nullptr, 0, res, (const DecodeDesc*)c.descs.p, nd);
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[3], st));
+        c.ev_pending[1] = true;
+    }
+    c.last_launches[1] = 1;
+    CU(cudaGetLastError());
+    DecodeResult* hr = (DecodeResult*)((u8*)c.pinned + 128);
+    CU(cudaMemcpyAsync(hr, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    harvest_timing(c, 1);
     return hr->fallback ? SNAPPY_B200_INVALID_INPUT : SNAPPY_B200_OK;
 }
 

@@ -107,6 +107,45 @@ def uncompress_shard_device(data, frag_offsets, out_len, out=None):
     return out
 
 
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None and t.numel() else 0) for t in tensors])
+
+
+def compress_shards_device(shards, total_lens, want_sizes=True):
+    """Batched compress_shard_device: all shards go through one kernel pass.
+    Returns a list of (bytes_view, frag_sizes)."""
+    count = len(shards)
+    dev = shards[0].device
+    outs = [torch.empty(maxlength_compressed(s.numel()), dtype=torch.uint8, device=dev) for s in shards]
+    sizes = [torch.empty(max(nfragments(s.numel()), 1), dtype=torch.int32, device=dev) for s in shards]
+    lens = (ctypes.c_size_t * count)(*[s.numel() for s in shards])
+    totals = (ctypes.c_uint64 * count)(*[int(t) for t in total_lens])
+    caps = (ctypes.c_size_t * count)(*[o.numel() for o in outs])
+    out_lens = (ctypes.c_size_t * count)()
+    for s in shards:
+        if not s.is_cuda or not s.is_contiguous():
+            raise ValueError("expected contiguous CUDA tensors")
+    with torch.cuda.device(dev):
+        _abi.lib().snappy_b200_init(dev.index)
+        _check(_abi.lib().snappy_b200_compress_shards_device(
+            _ptr_array(shards), lens, totals, count, _ptr_array(outs), caps, out_lens,
+            _ptr_array(sizes) if want_sizes else None, _stream_ptr(dev)))
+    return [(outs[k][: out_lens[k]], sizes[k][: nfragments(shards[k].numel())]) for k in range(count)]
+
+
+def uncompress_shards_device(datas, frag_offsets, out_lens):
+    """Batched uncompress_shard_device.  Returns the list of decoded runs."""
+    count = len(datas)
+    dev = datas[0].device
+    outs = [torch.empty(int(n), dtype=torch.uint8, device=dev) for n in out_lens]
+    lens = (ctypes.c_size_t * count)(*[int(n) for n in out_lens])
+    with torch.cuda.device(dev):
+        _abi.lib().snappy_b200_init(dev.index)
+        _check(_abi.lib().snappy_b200_uncompress_shards_device(
+            _ptr_array(datas), _ptr_array(frag_offsets), lens, count, _ptr_array(outs), _stream_ptr(dev)))
+    return outs
+
+
 def compress_batched_device(src, in_offsets, in_sizes, out=None, out_offsets=None):
     """One independent stream per page.  in_offsets int64[count], in_sizes int32[count] (device).
     Returns (out, out_offsets, out_sizes)."""

@@ -60,6 +60,16 @@ class CudaCodec:
         from . import device
         return device.uncompress_shard_device(data, frag_offsets, out_len)
 
+    # batched forms: every shard a rank holds goes through ONE kernel pass, which keeps the GPU
+    # full when the rank's work is many small shards (W streams x 1/W each)
+    def compress_shards(self, shards, total_lens):
+        from . import device
+        return device.compress_shards_device(shards, total_lens)
+
+    def uncompress_shards(self, datas, frag_offsets, out_lens):
+        from . import device
+        return device.uncompress_shards_device(datas, frag_offsets, out_lens)
+
 
 def compress_streams(shards, total_lens, codec, group=None):
     """shards[s]: this rank's run of stream s (uint8 tensor), total_lens[s]: stream s's total length.
@@ -71,11 +81,12 @@ def compress_streams(shards, total_lens, codec, group=None):
     rank = dist.get_rank(group)
     assert len(shards) == world == len(total_lens)
     dev = shards[0].device
-    segs, frag_sizes = [], []
-    for s in range(world):
-        seg, sizes = codec.compress_shard(shards[s], total_lens[s])
-        segs.append(seg)
-        frag_sizes.append(sizes.to(torch.int64))
+    if hasattr(codec, "compress_shards"):
+        pairs = codec.compress_shards(shards, total_lens)
+    else:
+        pairs = [codec.compress_shard(shards[s], total_lens[s]) for s in range(world)]
+    segs = [p[0] for p in pairs]
+    frag_sizes = [p[1].to(torch.int64) for p in pairs]
     # exchange 1: compressed byte counts (the path's only data-dependent global fact)
     mine = torch.tensor([int(x.numel()) for x in segs], dtype=torch.int64, device=dev)
     matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
@@ -139,12 +150,14 @@ def uncompress_streams(stream, index, total_len, codec, group=None):
     n_out = [int(n_mat[s][rank]) for s in range(world)]
     offs = torch.empty(sum(n_out), dtype=torch.int64, device=dev)
     dist.all_to_all_single(offs, torch.cat(rel), n_out, n_in, group=group)
-    runs, a, b = [], 0, 0
+    datas, fos, out_lens, a, b = [], [], [], 0, 0
     for s in range(world):
         lo, hi = shard_bounds(lens[s], world)[rank]
-        data = recv[a: a + out_splits[s]]
-        fo = offs[b: b + n_out[s]].contiguous()
-        runs.append(codec.uncompress_shard(data, fo, hi - lo))
+        datas.append(recv[a: a + out_splits[s]])
+        fos.append(offs[b: b + n_out[s]])
+        out_lens.append(hi - lo)
         a += out_splits[s]
         b += n_out[s]
-    return runs
+    if hasattr(codec, "uncompress_shards"):
+        return codec.uncompress_shards(datas, fos, out_lens)
+    return [codec.uncompress_shard(datas[s], fos[s].contiguous(), out_lens[s]) for s in range(world)]

@@ -268,3 +268,30 @@ def test_host_api_pipelined_paths(snappy, oracle):
     want = oracle.compress_np(raw)
     assert got.size == want.size and np.array_equal(got, want)
     assert np.array_equal(snappy.uncompress_np(want), raw)
+
+
+def test_batched_shard_api(dev, oracle):
+    """several shards of different streams (different totals, ragged tails, a tiny-table stream) in
+    one kernel pass == the same shards one by one == the oracle"""
+    from snappy_jl_b200 import synth
+    import torch
+    streams = [synth.mix(9, seed=31, tail=555), synth.mix(3, seed=32), np.frombuffer(read_data("urls.10K"), dtype=np.uint8),
+               np.frombuffer(b"tiny stream with a small table " * 20, dtype=np.uint8)]
+    cuts = [(0, 4 * 65536), (4 * 65536, streams[0].size), (0, streams[1].size), (65536, streams[2].size), (0, streams[3].size)]
+    which = [0, 0, 1, 2, 3]
+    shards = [to_dev(streams[w][a:b]) for w, (a, b) in zip(which, cuts)]
+    totals = [streams[w].size for w in which]
+    res = dev.compress_shards_device(shards, totals)
+    datas, fos, lens = [], [], []
+    for (seg, sizes), w, (a, b) in zip(res, which, cuts):
+        f0 = a // 65536
+        nf = (b - a + 65535) // 65536
+        want, wsizes = oracle.compress_fragments(streams[w], streams[w].size, f0, nf)
+        assert np.array_equal(seg.cpu().numpy(), want)
+        assert np.array_equal(sizes.cpu().numpy().astype(np.uint32), wsizes)
+        datas.append(seg)
+        fos.append(to_dev(np.concatenate([[0], np.cumsum(wsizes.astype(np.int64))])))
+        lens.append(b - a)
+    outs = dev.uncompress_shards_device(datas, fos, lens)
+    for o, w, (a, b) in zip(outs, which, cuts):
+        assert np.array_equal(o.cpu().numpy(), streams[w][a:b])
