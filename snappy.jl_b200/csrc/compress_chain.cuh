@@ -27,6 +27,7 @@ namespace sb200 {
 
 constexpr u32 kChainPoEntries = 352;  // probe offsets of the skip heuristic (:162-172)
 constexpr u32 kPrefetchLanes = 8;       // post-copy candidates prefetched into L1 (ends ip+4 .. ip+11)
+constexpr u32 kFirstProbes = 8;        // lanes in the first round of a scan
 constexpr u32 kStreamAhead = 2048;     // ip-side bytes are pulled into L2 this far ahead
 constexpr u32 kTailPad = 256;         // zero bytes behind the padded copy of the shard's last fragment
 
@@ -179,8 +180,10 @@ struct Chain {
 
     // ---- one scan round over 32 probes (lane i = i-th probe of the round) ------------------------
     // returns 1 = hit (ip/cand set), 2 = bail to the remainder, 0 = no hit (all 32 inserted)
-    __device__ __forceinline__ int scan_round(u32 p, u32 pn, u32& ip, u32& cand) {
-        const bool valid = (int)pn <= lim;  // :175 (checked before probing p)
+    // `act`: lanes that take part (the first round of a scan uses only kFirstProbes lanes: most scans
+    // hit within a few probes, and every probing lane costs a candidate-side cache line)
+    __device__ __forceinline__ int scan_round(u32 p, u32 pn, bool act, u32& ip, u32& cand) {
+        const bool valid = act && (int)pn <= lim;  // :175 (checked before probing p)
         const u32 W = ldg32u(F + (valid ? p : 0u));
         const u32 H = hash(W);
         const u32 mp = __match_any_sync(kFullMask, valid ? H : (0x80000000u | lane));
@@ -192,7 +195,7 @@ struct Chain {
         if (prior) c = fp;
         const bool eq = valid && (ldg32u(F + c) == W);  // :193
         const u32 hitm = __ballot_sync(kFullMask, eq);
-        const u32 invm = __ballot_sync(kFullMask, !valid);
+        const u32 invm = __ballot_sync(kFullMask, act && !valid);
         const u32 fh = hitm ? (u32)__ffs((int)hitm) - 1u : 32u;
         const u32 fi = invm ? (u32)__ffs((int)invm) - 1u : 32u;
         if (fh >= fi && fi < 32) return 2;
@@ -200,7 +203,7 @@ struct Chain {
         const u32 upto = (last >= 31) ? kFullMask : ((2u << last) - 1u);
         const u32 after = (lane >= 31) ? 0u : ~((2u << lane) - 1u);
         // commit inserts of probes 0..last; on equal hashes the later probe wins (:191)
-        if (lane <= last && (mp & after & upto) == 0) tput(H, p);
+        if (valid && lane <= last && (mp & after & upto) == 0) tput(H, p);
         __syncwarp();
         if (fh < 32) {
             ip = __shfl_sync(kFullMask, p, fh);
@@ -227,9 +230,11 @@ struct Chain {
                 // ---------------- scan, :162-194
                 const u32 s = ip + 1;
                 u32 cand = 0;
-                int res = scan_round(s + lane, s + lane + 1, ip, cand);  // first 32 probes: stride 1
-                for (u32 base = 32; res == 0; base += 32)
-                    res = scan_round(s + g_probe_offsets[base + lane], s + g_probe_offsets[base + lane + 1], ip, cand);
+                // the first 32 probes have stride 1; probe k >= 32 sits at s + g_probe_offsets[k]
+                int res = scan_round(s + lane, s + lane + 1, lane < kFirstProbes, ip, cand);
+                for (u32 base = kFirstProbes; res == 0; base += 32)
+                    res = scan_round(s + g_probe_offsets[base + lane], s + g_probe_offsets[base + lane + 1], true,
+                                     ip, cand);
                 if (res == 2) break;
                 // ---------------- copy chain, :211-239
                 // One candidate-side memory round trip per copy: lane l compares byte l of the

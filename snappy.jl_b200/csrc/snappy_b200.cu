@@ -47,7 +47,7 @@ struct DevBuf {
 };
 
 constexpr int kMaxPipeChunks = 72;                 // 4 GiB / 64 MiB, plus slack
-constexpr size_t kPipeChunkFrags = 4096;           // fragments per pipeline chunk (256 MiB)
+constexpr size_t kPipeChunkFragsDefault = 4096;    // fragments per pipeline chunk (256 MiB)
 
 struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
@@ -57,6 +57,7 @@ struct Options {
     int l2_chains = 14;         // extra persistent warps per SM with the table in global memory (L2)
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
+    int pipe_chunk_frags = (int)kPipeChunkFragsDefault;  // host-buffer API pipeline granularity
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
 };
@@ -350,6 +351,7 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
     CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
     // host-buffer API: decode in ranges and send each finished range down while the next decodes
+    const size_t kPipeChunkFrags = (size_t)c.opt.pipe_chunk_frags;
     const bool ranged = host_out && c.opt.host_pipeline && nfrag > kPipeChunkFrags;
     const u32 step = ranged ? (u32)kPipeChunkFrags : nfrag;
     int ri = 0;
@@ -616,6 +618,7 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
 // previous one's bytes as soon as it has landed, and its bytes go back down on a third stream
 // while the next chunk compresses.  Only the chunk totals (8 bytes each) are read by the host.
 int compress_host_pipelined(Context& c, const u8* in, size_t n, u8* out, size_t* out_len) {
+    const size_t kPipeChunkFrags = (size_t)c.opt.pipe_chunk_frags;
     const size_t need = snappy_b200_max_compressed_length(n);
     const u32 nfrag = (u32)((n + kBlockSize - 1) / kBlockSize);
     const int nchunks = (int)((nfrag + kPipeChunkFrags - 1) / kPipeChunkFrags);
@@ -682,7 +685,7 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
     Context& c = g_ctx;
-    if (c.opt.compress_variant == 0 && c.opt.host_pipeline && n > kPipeChunkFrags * kBlockSize)
+    if (c.opt.compress_variant == 0 && c.opt.host_pipeline && n > (size_t)c.opt.pipe_chunk_frags * kBlockSize)
         return compress_host_pipelined(c, in, n, out, out_len);
     CU(c.stage_in.ensure(n + 16));
     CU(c.stage_out.ensure(need + 16));
@@ -994,6 +997,10 @@ void snappy_b200_set_option(const char* name, int value) {
     else if (!strcmp(name, "prefetch_lanes")) g_ctx.opt.prefetch_lanes = value;
     else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
     else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
+    else if (!strcmp(name, "pipe_chunk_frags")) {
+        // at most kMaxPipeChunks chunks for the largest stream (2^32 bytes = 65536 fragments)
+        g_ctx.opt.pipe_chunk_frags = value < 1024 ? 1024 : value;
+    }
     else if (!strcmp(name, "decode_occupancy")) g_ctx.opt.decode_occupancy = value;
     else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
 }
