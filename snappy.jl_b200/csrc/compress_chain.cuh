@@ -57,12 +57,11 @@ __global__ void k_init_probe_offsets() {
 
 template <bool kSmemTable>
 struct Chain {
-    static constexpr u32 kSpec = 32u;  // end positions pre-probed per copy
     const u8* F;     // fragment bytes (global, >= 64 readable bytes past n)
     u16* T;          // hash table, position per hash, 0 == empty (global variant)
     u32 Ts;          // shared-space address of the table (shared variant)
     u8* out;         // scratch slot of this fragment
-    u32 n, shift, lane, op, nrec, pf_lanes;
+    u32 n, shift, lane, op, nrec, spec;  // spec: end positions pre-probed per copy (<= 32)
     int lim;
     u32 r_lit, r_cpy;  // lane k parks record k: (lit_from | ip << 16), (cand | M << 16)
 
@@ -254,9 +253,9 @@ struct Chain {
                     const u32 Wme = __funnelshift_r(elo, ehi, (u32)ea << 3);                 // bytes [e-1, e+3)
                     const u32 We = __funnelshift_rc(elo, ehi, (((u32)ea & 3u) << 3) + 8u);  // bytes [e, e+4)
                     const u32 He = hash(We), Hme = hash(Wme);
-                    // global-table warps pre-probe only the kSpec shortest copies (M = 4 .. 3+kSpec, the
+                    // only the `spec` shortest copies (M = 4 .. 3+spec) are pre-probed (the
                     // bulk of all copies): 32-lane gathers from L2 are what slows them down
-                    const u32 te = (kSpec == 32 || lane < kSpec) ? tget(He) : 0u;
+                    const u32 te = (lane < spec) ? tget(He) : 0u;
                     const u32 ce = (Hme == He) ? (e - 1) : te;  // :233 is visible to :234
                     u32 M = neq ? (u32)__ffs((int)neq) - 1u : 32u;
                     if (!verified && M < 4) break;  // :238 no match at ip: back to scanning from ip+1
@@ -276,7 +275,7 @@ struct Chain {
                     lit_from = ip;
                     if ((int)ip >= lim) { finished = true; break; }  // :222
                     u32 c2;
-                    if (M < 4 + kSpec) {
+                    if (M < 4 + spec) {
                         const u32 owner = M - 4;
                         c2 = __shfl_sync(kFullMask, ce, owner);
                         if (lane == owner) {
@@ -332,11 +331,13 @@ struct ShardDesc {
 // <= 227 KiB) where seven 1-warp CTAs would not.  Warps never synchronise with each other.
 //   tail_copy : padded copy of the shard's LAST fragment (so reads may run past its end)
 //   gtables   : kSmemTable == false: one 32 KiB table per warp in global memory
+// The global-table variant is compiled for 3 CTAs of <= 14 warps per SM (<= 48 registers): many slow
+// chains; the shared-table variant runs as one CTA per SM.
 template <bool kSmemTable>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kSmemTable ? 224 : 448, kSmemTable ? 1 : 3)
 k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
-                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 pf_lanes, u32 reserve,
+                 u32* __restrict__ counter, u16* __restrict__ gtables, u32 spec_lanes, u32 reserve,
                  const ShardDesc* __restrict__ descs, u32 ndesc) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
@@ -381,7 +382,7 @@ k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shif
         ch.n = n;
         ch.shift = fshift;
         ch.lane = lane;
-        ch.pf_lanes = pf_lanes;
+        ch.spec = spec_lanes;
         ch.run();
         if (lane == 0) frag_sizes[frag] = ch.op;
         __syncwarp();

@@ -53,8 +53,12 @@ struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
     int l2_reserve = 2;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
-    int prefetch_lanes = 0;     // post-copy candidates prefetched into L1 per step
-    int l2_chains = 14;         // extra persistent warps per SM with the table in global memory (L2)
+    int ring_smem = 4096;       // history ring per shared-table warp (bytes, power of two >= 1024)
+    int ring_l2 = 2048;         // history ring per global-table warp
+    int spec_smem = 32;         // copy end positions pre-probed per step by shared-table warps (1..32)
+    int spec_l2 = 16;           // same for global-table warps (each probing lane costs an L1tex wavefront)
+    int l2_chains = 14;         // warps per CTA of the global-table (L2) kernel, <= 14
+    int l2_ctas = 1;            // CTAs per SM of that kernel (1..3): l2_ctas x l2_chains extra chains per SM
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
     int pipe_chunk_frags = (int)kPipeChunkFragsDefault;  // host-buffer API pipeline granularity
@@ -135,8 +139,13 @@ int ctx_init_locked(int device) {
                             (int)kCompressSmemBytes));
     CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompress2SmemBytes));
-    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(7 * kMaxTableEntries * 2)));
+    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // both kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
+    // CTAs fit next to the shared-table CTA
+    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     k_init_probe_offsets<<<1, 32>>>();
     CU(cudaGetLastError());
     CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
@@ -230,22 +239,22 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
     const u32 wa = (u32)c.opt.smem_chains, wb = (u32)c.opt.l2_chains;
-    u32 ctas_a = (nfrag + wa - 1) / wa;
+    u32 ctas_a = wa ? (nfrag + wa - 1) / wa : 0u;  // smem_chains == 0: global-table warps only (profiling)
     if (ctas_a > (u32)c.sm_count) ctas_a = (u32)c.sm_count;
     const u32 warps_a = ctas_a * wa;
     const u32 reserve = (u32)c.opt.l2_reserve * warps_a;
-    const u32 ctas_b = (wb && nfrag > warps_a + reserve) ? (u32)c.sm_count : 0u;
+    const u32 ctas_b = (wb && (nfrag > warps_a + reserve || !wa)) ? (u32)(c.sm_count * c.opt.l2_ctas) : 0u;
     if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * kMaxTableEntries * 2));
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
-    k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
+    if (ctas_a) k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
         d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
-        (u32)c.opt.prefetch_lanes, 0u, descs, ndesc);
+        (u32)c.opt.spec_smem, 0u, descs, ndesc);
     *launches += 1;
     if (ctas_b) {
         CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
         k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
             d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
-            (u16*)c.gtables.p, (u32)c.opt.prefetch_lanes, reserve, descs, ndesc);
+            (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -992,9 +1001,16 @@ void snappy_b200_set_option(const char* name, int value) {
     if (!name) return;
     if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
-    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 1 ? 1 : (value > 7 ? 7 : value);
-    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 16 ? 16 : value);
-    else if (!strcmp(name, "prefetch_lanes")) g_ctx.opt.prefetch_lanes = value;
+    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
+    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
+        int r = 1024;
+        while (r < value && r < 32768) r <<= 1;
+        (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
+    }
+    else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
     else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
     else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
     else if (!strcmp(name, "pipe_chunk_frags")) {
