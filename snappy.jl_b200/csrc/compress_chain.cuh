@@ -212,6 +212,27 @@ struct Chain {
         return 0;
     }
 
+    // ---- :242-248: pending records, then the remainder literal (up to the whole fragment: emitted directly)
+    __device__ __forceinline__ void finish(u32 lit_from) {
+        if (nrec) flush();
+        if (lit_from < n) {
+            const u32 ll = n - lit_from, nm1 = ll - 1;
+            const u32 lh = ll < 60 ? 1u : (nm1 <= 0xffu ? 2u : (nm1 <= 0xffffu ? 3u : 4u));
+            if (lane == 0) {
+                if (ll < 60) {
+                    out[op] = (u8)(nm1 << 2);
+                } else {
+                    out[op] = (u8)((59 + (lh - 1)) << 2);
+                    out[op + 1] = (u8)nm1;
+                    if (lh > 2) out[op + 2] = (u8)(nm1 >> 8);
+                    if (lh > 3) out[op + 3] = (u8)(nm1 >> 16);
+                }
+            }
+            for (u32 k = lane; k < ll; k += 32) out[op + lh + k] = __ldg(F + lit_from + k);
+            op += lh + ll;
+        }
+    }
+
     // ---- the fragment --------------------------------------------------------------------------
     __device__ __forceinline__ void run() {
         // keep these in registers: without the barrier ptxas re-derives them (64-bit min, S2R,
@@ -297,23 +318,7 @@ struct Chain {
                 }
             }
         }
-        if (nrec) flush();
-        if (lit_from < n) {  // :242-248 remainder literal (up to the whole fragment: emitted directly)
-            const u32 ll = n - lit_from, nm1 = ll - 1;
-            const u32 lh = ll < 60 ? 1u : (nm1 <= 0xffu ? 2u : (nm1 <= 0xffffu ? 3u : 4u));
-            if (lane == 0) {
-                if (ll < 60) {
-                    out[op] = (u8)(nm1 << 2);
-                } else {
-                    out[op] = (u8)((59 + (lh - 1)) << 2);
-                    out[op + 1] = (u8)nm1;
-                    if (lh > 2) out[op + 2] = (u8)(nm1 >> 8);
-                    if (lh > 3) out[op + 3] = (u8)(nm1 >> 16);
-                }
-            }
-            for (u32 k = lane; k < ll; k += 32) out[op + lh + k] = __ldg(F + lit_from + k);
-            op += lh + ll;
-        }
+        finish(lit_from);
     }
 };
 

@@ -1,0 +1,381 @@
+// compress_window.cuh -- K1w: window-parallel fragment compressor, one warp per fragment.
+//
+// Same serial decisions as the reference (src/internal.jl:127-250), evaluated 32 positions at a
+// time instead of one decision per dependent memory round trip (compress_chain.cuh):
+//
+//   * A round looks at the window [a, a+32), lane l <-> position q = a + l.  Every lane evaluates
+//     its position as if the chain arrived there: hash of the 4 bytes at q (:94), table lookup
+//     against the table AS OF THE ROUND START, and the common prefix of candidate and q over 16
+//     bytes (find_match_length, :344-387, capped).
+//   * The real chain is then followed through the window with warp-uniform bit masks:
+//       arrival after a copy (:228-238): insert q-1 and q, a match of >= 4 bytes is the next copy,
+//         otherwise a scan starts at q+1;
+//       scan (:167-194): every position up to the first hit is inserted; the hit emits the pending
+//         literal and the copy.
+//     A copy of m < 16 bytes jumps to lane l + m of the same window, so a round typically resolves
+//     3-8 reference steps.
+//   * Exactness: a lane's lookup equals the reference's iff no position inserted since the round
+//     start has its hash.  All those positions lie in the window below it, so a lane whose hash
+//     equals ANY lower lane's is never trusted: the round ends there and the next round starts at
+//     that position as lane 0, which sees the committed table.  Inserts of the path are committed
+//     at the end of the round, the highest position winning among equal hashes (:191).
+//   * Left to the step-wise code of compress_chain.cuh: copies of >= 16 bytes (the whole warp
+//     extends the match, 32 bytes per ballot) and scans that reach the stride > 1 part of the skip
+//     heuristic (probe 32 onwards, :162-172) - incompressible data.
+//
+// Data path: the last `ring` bytes of the fragment up to ip + 64 live in a per-warp shared-memory
+// ring (staged 512 bytes at a time with 16-byte loads), which serves every ip-side read and the
+// candidates that are recent; older candidates are gathered from L1/L2 (first 4 bytes, then the
+// remaining 12 for lanes that match).  tools/emulate_window.c is the CPU model of this file; it is
+// checked against the oracle on every fixture.
+#pragma once
+#include "compress_chain.cuh"
+
+namespace sb200 {
+
+constexpr u32 kRingChunk = 512;  // bytes staged per step (one 16-byte load per lane)
+constexpr u32 kRingAhead = 64;   // bytes past the window start that must be resident
+
+template <bool kSmemTable>
+struct Win : Chain<kSmemTable> {
+    using Base = Chain<kSmemTable>;
+    using Base::F;
+    using Base::lane;
+    using Base::lim;
+    using Base::n;
+    // ring: positions [lo, hi) of the fragment at Rs + (position & rmask); hi is a multiple of 512
+    u32 Rs, rmask, lo, hi, nstage;
+    bool aligned16;
+
+    static __device__ __forceinline__ u32 lds32(u32 a) {
+        u32 v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        return v;
+    }
+    // unaligned 32-bit load at position p (lo <= p, p + 8 <= hi)
+    __device__ __forceinline__ u32 ring32u(u32 p) const {
+        const u32 q = p & ~3u;
+        return __funnelshift_r(lds32(Rs + (q & rmask)), lds32(Rs + ((q + 4u) & rmask)), p << 3);
+    }
+    // stage chunks until [.., upto) is resident or the fragment is exhausted
+    __device__ __forceinline__ void stage_to(u32 upto) {
+        u32 from = lo;
+        if (upto > hi + rmask + 1u) {  // a long copy ran past the ring: everything older is dropped
+            hi = (upto - (rmask + 1u)) & ~(kRingChunk - 1u);
+            from = hi;
+        }
+        while (hi < upto && hi < nstage) {
+            const u32 p = hi + lane * 16u;
+            uint4 v;
+            if (aligned16) {
+                v = __ldg(reinterpret_cast<const uint4*>(F + p));
+            } else {
+                v.x = ldg32u(F + p);
+                v.y = ldg32u(F + p + 4);
+                v.z = ldg32u(F + p + 8);
+                v.w = ldg32u(F + p + 12);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + (p & rmask)), "r"(v.x), "r"(v.y),
+                         "r"(v.z), "r"(v.w)
+                         : "memory");
+            hi += kRingChunk;
+        }
+        lo = hi > rmask + 1u ? hi - (rmask + 1u) : 0u;
+        if (lo < from) lo = from;
+        __syncwarp();
+    }
+
+    // whole-warp match extension from `M` known equal bytes (find_match_length, :344-387)
+    __device__ __forceinline__ u32 extend(u32 ip, u32 cand, u32 M) const {
+        const u8* pa = F + cand + lane;
+        const u8* pb = F + ip + lane;
+        while (ip + M < n) {
+            const u32 nq = __ballot_sync(kFullMask, __ldg(pa + M) != __ldg(pb + M));
+            if (nq) {
+                M += (u32)__ffs((int)nq) - 1u;
+                break;
+            }
+            M += 32;
+        }
+        if (ip + M > n) M = n - ip;
+        return M;
+    }
+
+    __device__ __forceinline__ void run_window() {
+        asm volatile("" : "+r"(this->n), "+r"(this->Ts), "+r"(this->shift), "+r"(Rs), "+r"(rmask));
+        this->op = 0;
+        this->nrec = 0;
+        this->r_lit = this->r_cpy = 0;
+        lim = (int)n - 16;  // ip_limit, :131
+        u32 lit_from = 0;
+        if (n >= kInputMargin) {
+            bool arrival = false;  // round starts with a post-copy arrival at a (else: scanning)
+            u32 a = 1, scan_s = 1;  // :162-163 the first scan starts at position 1
+            for (;;) {
+                // ------------- scans past 32 probes: stride > 1, step-wise (incompressible data)
+                if (!arrival && a - scan_s >= 32u) {
+                    u32 ip = 0, cand = 0;
+                    int res = 0;
+                    for (u32 base = 32; res == 0; base += 32)
+                        res = this->scan_round(scan_s + g_probe_offsets[base + lane],
+                                               scan_s + g_probe_offsets[base + lane + 1], true, ip, cand);
+                    if (res == 2) break;
+                    const u32 M = extend(ip, cand, 4);
+                    this->keep(lit_from, ip, cand, M);  // :200,:217
+                    a = ip + M;
+                    lit_from = a;
+                    if ((int)a >= lim) break;  // :222
+                    arrival = true;
+                    continue;
+                }
+                // ------------- lane evaluation against the table as of the round start
+                if (a + kRingAhead > hi) stage_to(a + kRingAhead);
+                if (arrival) {  // :233 the position before an arrival is inserted first
+                    if (lane == 0) this->tput(this->hash(ring32u(a - 1u)), a - 1u);
+                    __syncwarp();
+                }
+                const u32 q = a + lane;
+                const bool V = (int)q < lim;
+                u32 B0, B1, B2, B3;
+                {
+                    const u32 qb = q & ~3u, sh = q << 3;
+                    const u32 w0 = lds32(Rs + (qb & rmask)), w1 = lds32(Rs + ((qb + 4u) & rmask)),
+                              w2 = lds32(Rs + ((qb + 8u) & rmask)), w3 = lds32(Rs + ((qb + 12u) & rmask)),
+                              w4 = lds32(Rs + ((qb + 16u) & rmask));
+                    B0 = __funnelshift_r(w0, w1, sh);
+                    B1 = __funnelshift_r(w1, w2, sh);
+                    B2 = __funnelshift_r(w2, w3, sh);
+                    B3 = __funnelshift_r(w3, w4, sh);
+                }
+                const u32 H = this->hash(B0);
+                const u32 t = V ? this->tget(H) : lo;
+                const u32 mp = __match_any_sync(kFullMask, V ? H : (0x80000000u | lane));
+                // candidate bytes, straight-line: recent candidates come from the ring (5 words), old
+                // ones from L1/L2 (2 words = the 4 bytes that decide a hit; the other 3 only on a hit)
+                const u32 nearp = (t >= lo) ? 1u : 0u;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(F + t);  // F need not be 4-byte aligned
+                const u32* g = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+                const u32 tb = t & ~3u, tsh = (nearp ? t : (u32)ga) << 3;
+                u32 c0, c1, c2 = 0, c3 = 0, c4 = 0;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "setp.ne.u32 p, %5, 0;\n"
+                    "@p ld.shared.u32 %0, [%6];\n"
+                    "@p ld.shared.u32 %1, [%7];\n"
+                    "@p ld.shared.u32 %2, [%8];\n"
+                    "@p ld.shared.u32 %3, [%9];\n"
+                    "@p ld.shared.u32 %4, [%10];\n"
+                    "@!p ld.global.nc.u32 %0, [%11];\n"
+                    "@!p ld.global.nc.u32 %1, [%11+4];\n"
+                    "}\n"
+                    : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+                    : "r"(nearp), "r"(Rs + (tb & rmask)), "r"(Rs + ((tb + 4u) & rmask)),
+                      "r"(Rs + ((tb + 8u) & rmask)), "r"(Rs + ((tb + 12u) & rmask)),
+                      "r"(Rs + ((tb + 16u) & rmask)), "l"(g)
+                    : "memory");
+                u32 C0 = __funnelshift_r(c0, c1, tsh);
+                const bool more = V && !nearp && C0 == B0;
+                if (__any_sync(kFullMask, more)) {
+                    if (more) {
+                        c2 = __ldg(g + 2);
+                        c3 = __ldg(g + 3);
+                        c4 = __ldg(g + 4);
+                    }
+                }
+                u32 m = 0;
+                {
+                    const u32 x0 = C0 ^ B0, x1 = __funnelshift_r(c1, c2, tsh) ^ B1,
+                              x2 = __funnelshift_r(c2, c3, tsh) ^ B2, x3 = __funnelshift_r(c3, c4, tsh) ^ B3;
+                    if (x0) m = ((u32)__ffs((int)x0) - 1u) >> 3;
+                    else if (x1) m = 4u + (((u32)__ffs((int)x1) - 1u) >> 3);
+                    else if (x2) m = 8u + (((u32)__ffs((int)x2) - 1u) >> 3);
+                    else if (x3) m = 12u + (((u32)__ffs((int)x3) - 1u) >> 3);
+                    else m = 16u;
+                    if (!V) m = 0;
+                }
+                const u32 vmask = __ballot_sync(kFullMask, V);
+                const u32 hitmask = __ballot_sync(kFullMask, m >= 4u);
+                const u32 dupmask = __ballot_sync(kFullMask, (mp & ((1u << lane) - 1u)) != 0u);
+                const u32 tm = (t << 16) | (m << 8);
+                // ------------- per-lane descriptor: what happens when the chain ARRIVES at this lane
+                //   bits 0-2 kind, 3-7 lane e of the event, 8-12 copy length, 16-31 candidate, bit 13 = a scan started
+                enum : u32 { K_COPY = 0, K_SLOW = 1, K_FIN = 2, K_NEXTSCAN = 3, K_NEXTARR = 4, K_LEAVE = 5 };
+                const u32 stop_all = ~vmask | dupmask | hitmask;
+                u32 desc, ins;
+                {
+                    const u32 lbit = 1u << lane;
+                    const u32 rest = (lane < 31u) ? (stop_all >> (lane + 1u)) : 0u;
+                    const u32 es = lane + (u32)__ffs((int)rest);  // first event lane of a scan from lane + 1
+                    const u32 ebit = 1u << (es & 31u);
+                    u32 kind, e;
+                    ins = lbit | (lbit >> 1);  // :233,:235
+                    if (hitmask & lbit) {
+                        kind = K_COPY;
+                        e = lane;
+                    } else if (!rest) {
+                        kind = K_LEAVE;
+                        e = 0;
+                        if (lane < 31u) ins |= ~0u << (lane + 1u);
+                    } else {
+                        e = es;
+                        ins |= (ebit - 1u) & (~0u << (lane + 1u));
+                        if (!(vmask & ebit)) kind = K_FIN;  // :175
+                        else if (dupmask & ebit) kind = K_NEXTSCAN;
+                        else {
+                            kind = K_COPY;
+                            ins |= ebit;  // :191
+                        }
+                    }
+                    if (lane && (dupmask & lbit)) {  // untrusted lane: the next round starts here
+                        kind = K_NEXTARR;
+                        e = lane;
+                        ins = 0;
+                    }
+                    const u32 r = __shfl_sync(kFullMask, tm, e);  // candidate and length of the copy at e
+                    if (kind == K_COPY && ((r >> 8) & 31u) == 16u) kind = K_SLOW;
+                    desc = kind | (e << 3) | ((hitmask & lbit) ? 0u : (1u << 13)) | (r & 0xffff1f00u);
+                }
+                // a round that starts inside a scan: the same from "lane -1", and the scan also stops
+                // where its probe count reaches 32 (:162-172)
+                u32 d, insacc, cur = 0;
+                if (arrival) {
+                    d = __shfl_sync(kFullMask, desc, 0);
+                    insacc = __shfl_sync(kFullMask, ins, 0);
+                } else {
+                    const u32 klim = 32u - (a - scan_s);  // 1..32
+                    const u32 limmask = klim < 32u ? ~((1u << klim) - 1u) : 0u;
+                    const u32 rest = stop_all | limmask;
+                    u32 kind, e = 0;
+                    if (!rest) {
+                        kind = K_LEAVE;
+                        insacc = ~0u;
+                    } else {
+                        e = (u32)__ffs((int)rest) - 1u;
+                        const u32 ebit = 1u << e;
+                        insacc = ebit - 1u;
+                        if (!(vmask & ebit)) kind = K_FIN;
+                        else if ((dupmask | limmask) & ebit) kind = K_NEXTSCAN;
+                        else {
+                            kind = K_COPY;
+                            insacc |= ebit;
+                        }
+                    }
+                    const u32 r = __shfl_sync(kFullMask, tm, e);
+                    if (kind == K_COPY && ((r >> 8) & 31u) == 16u) kind = K_SLOW;
+                    d = kind | (e << 3) | (r & 0xffff1f00u);  // bit 13 clear: scan_s stays
+                }
+                // ------------- follow the chain through the window (warp-uniform)
+                for (;;) {
+                    if (d & (1u << 13)) scan_s = a + cur + 1u;  // :162 a new scan started behind lane cur
+                    if ((d & 7u) != K_COPY) break;
+                    const u32 e = (d >> 3) & 31u, me = (d >> 8) & 31u;
+                    this->keep(lit_from, a + e, d >> 16, me);  // :200,:217
+                    cur = e + me;
+                    lit_from = a + cur;
+                    if ((int)lit_from >= lim) {  // :222
+                        d = K_FIN;
+                        break;
+                    }
+                    if (cur >= 32u) {
+                        d = K_NEXTARR | (1u << 14);  // arrival beyond the window
+                        break;
+                    }
+                    d = __shfl_sync(kFullMask, desc, cur);
+                    insacc |= __shfl_sync(kFullMask, ins, cur);
+                }
+                const u32 kind = d & 7u, ev = (d >> 3) & 31u;
+                const u32 ins_all = insacc;
+                // ------------- commit the inserts of the path; the highest position wins (:191)
+                if (((ins_all >> lane) & 1u) && (mp & ins_all & ~((2u << lane) - 1u)) == 0u) this->tput(H, q);
+                __syncwarp();
+                if (kind == K_SLOW) {  // copy of >= 16 bytes: the whole warp extends it
+                    const u32 ip = a + ev, cand = d >> 16;
+                    const u32 M = extend(ip, cand, 16);
+                    this->keep(lit_from, ip, cand, M);
+                    a = ip + M;
+                    lit_from = a;
+                    if ((int)a >= lim) break;
+                    arrival = true;
+                    continue;
+                }
+                if (kind == K_FIN) break;
+                if (kind == K_LEAVE) {
+                    arrival = false;
+                    a += 32u;
+                } else if (kind == K_NEXTSCAN) {
+                    arrival = false;
+                    a += ev;
+                } else {  // K_NEXTARR: at an untrusted lane of this window, or beyond it
+                    arrival = true;
+                    a = (d & (1u << 14)) ? lit_from : a + ev;
+                }
+            }
+        }
+        this->finish(lit_from);
+    }
+};
+
+// Persistent warps, as k_compress_chain; each warp additionally owns `ring_bytes` of shared memory
+// (behind the tables for the shared-table variant).
+template <bool kSmemTable>
+__global__ void __launch_bounds__(kSmemTable ? 224 : 448, kSmemTable ? 1 : 2)
+k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
+                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
+                  u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
+                  const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes) {
+    extern __shared__ __align__(128) u8 smem[];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarp = blockDim.x >> 5;
+    const u32 gwarp = blockIdx.x * nwarp + warp;
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * kMaxTableEntries
+                        : gtables + (size_t)gwarp * kMaxTableEntries;
+    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * kMaxTableEntries * 2u : 0u) + warp * ring_bytes;
+    const u32 lane = lane_id();
+    for (;;) {
+        if (reserve && *reinterpret_cast<volatile u32*>(counter) + reserve >= nfrag) break;
+        u32 frag = 0;
+        if (lane == 0) frag = atomicAdd(counter, 1u);
+        frag = __shfl_sync(kFullMask, frag, 0);
+        if (frag >= nfrag) break;
+        const u8* sbase = g_in;
+        const u8* stail = tail_copy;
+        u64 slen = shard_len;
+        u32 local = frag, lastf = nfrag - 1, fshift = shift;
+        if (descs) {
+            u32 k = 0;
+            while (k + 1 < ndesc && descs[k + 1].frag_begin <= frag) k++;
+            sbase = descs[k].ptr;
+            stail = descs[k].tail;
+            slen = descs[k].len;
+            local = frag - descs[k].frag_begin;
+            lastf = descs[k].nfrag - 1;
+            fshift = descs[k].shift;
+        }
+        const u64 start = (u64)local * kBlockSize;
+        const u32 n = (u32)((slen - start < kBlockSize) ? (slen - start) : kBlockSize);
+        const u32 entries = 1u << (32 - fshift);
+        uint4* t4 = reinterpret_cast<uint4*>(T);
+        for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        Win<kSmemTable> ch;
+        ch.F = (local == lastf) ? stail : sbase + start;
+        ch.T = T;
+        ch.Ts = kSmemTable ? smem_u32(T) : 0u;
+        ch.out = scratch + (u64)frag * kSlotStride;
+        ch.n = n;
+        ch.shift = fshift;
+        ch.lane = lane;
+        ch.spec = 0;
+        ch.Rs = ring;
+        ch.rmask = ring_bytes - 1u;
+        ch.lo = ch.hi = 0;
+        ch.nstage = (n + kRingChunk - 1u) & ~(kRingChunk - 1u);
+        ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
+        ch.run_window();
+        if (lane == 0) frag_sizes[frag] = ch.op;
+        __syncwarp();
+    }
+}
+
+}  // namespace sb200

@@ -16,6 +16,7 @@
 
 #include "compress.cuh"
 #include "compress_chain.cuh"
+#include "compress_window.cuh"
 #include "decompress.cuh"
 #include "parse.cuh"
 
@@ -52,9 +53,10 @@ constexpr size_t kPipeChunkFragsDefault = 4096;    // fragments per pipeline chu
 struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
-    int l2_reserve = 2;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
-    int ring_smem = 4096;       // history ring per shared-table warp (bytes, power of two >= 1024)
-    int ring_l2 = 2048;         // history ring per global-table warp
+    int l2_reserve = 1;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
+    int window = 1;             // 1 = window-parallel kernel (compress_window.cuh), 0 = step-wise chain kernel
+    int ring_smem = 2048;       // history ring per shared-table warp (bytes, power of two >= 1024)
+    int ring_l2 = 1024;         // history ring per global-table warp
     int spec_smem = 32;         // copy end positions pre-probed per step by shared-table warps (1..32)
     int spec_l2 = 16;           // same for global-table warps (each probing lane costs an L1tex wavefront)
     int l2_chains = 14;         // warps per CTA of the global-table (L2) kernel, <= 14
@@ -104,6 +106,32 @@ int fail_cuda(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
 
+// tuning knobs (snappy_b200_set_option / SNAPPY_B200_OPTIONS); caller holds the context mutex
+void apply_option(const char* name, int value) {
+    if (!name) return;
+    if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
+    else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
+    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
+    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
+        int r = 1024;
+        while (r < value && r < 32768) r <<= 1;
+        (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
+    }
+    else if (!strcmp(name, "window")) g_ctx.opt.window = value;
+    else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
+    else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
+    else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
+    else if (!strcmp(name, "pipe_chunk_frags")) {
+        // at most kMaxPipeChunks chunks for the largest stream (2^32 bytes = 65536 fragments)
+        g_ctx.opt.pipe_chunk_frags = value < 1024 ? 1024 : value;
+    }
+    else if (!strcmp(name, "decode_occupancy")) g_ctx.opt.decode_occupancy = value;
+    else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
+}
+
 int ctx_init_locked(int device) {
     Context& c = g_ctx;
     if (c.ready) return SNAPPY_B200_OK;
@@ -142,6 +170,12 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // both kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
     // CTAs fit next to the shared-table CTA
+    CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -162,6 +196,19 @@ int ctx_init_locked(int device) {
     for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
     CU(c.result.ensure(256));
     c.ready = true;
+    // tuning knobs from the environment: SNAPPY_B200_OPTIONS="name=value,name=value" (see set_option)
+    if (const char* env = getenv("SNAPPY_B200_OPTIONS")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t comma = e.find(',', pos);
+            if (comma == std::string::npos) comma = e.size();
+            const std::string kv = e.substr(pos, comma - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos) apply_option(kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1));
+            pos = comma + 1;
+        }
+    }
     return SNAPPY_B200_OK;
 }
 
@@ -246,15 +293,29 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     const u32 ctas_b = (wb && (nfrag > warps_a + reserve || !wa)) ? (u32)(c.sm_count * c.opt.l2_ctas) : 0u;
     if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * kMaxTableEntries * 2));
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
-    if (ctas_a) k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
-        d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
-        (u32)c.opt.spec_smem, 0u, descs, ndesc);
+    const bool window = c.opt.window != 0;
+    const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
+    if (ctas_a) {
+        if (window)
+            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
+                ndesc, ra);
+        else
+            k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
+                (u32)c.opt.spec_smem, 0u, descs, ndesc);
+    }
     *launches += 1;
     if (ctas_b) {
         CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-        k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
-            d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
-            (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
+        if (window)
+            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * rb, c.side>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
+                reserve, descs, ndesc, rb);
+        else
+            k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
+                (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -996,29 +1057,10 @@ int snappy_b200_last_launch_count(int which) {
     return (which == 0 || which == 1) ? g_ctx.last_launches[which] : 0;
 }
 
+
 void snappy_b200_set_option(const char* name, int value) {
     std::unique_lock<std::mutex> lk(g_ctx.mu);
-    if (!name) return;
-    if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
-    else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
-    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
-    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 14 ? 14 : value);
-    else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
-    else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
-    else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
-        int r = 1024;
-        while (r < value && r < 32768) r <<= 1;
-        (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
-    }
-    else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
-    else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
-    else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
-    else if (!strcmp(name, "pipe_chunk_frags")) {
-        // at most kMaxPipeChunks chunks for the largest stream (2^32 bytes = 65536 fragments)
-        g_ctx.opt.pipe_chunk_frags = value < 1024 ? 1024 : value;
-    }
-    else if (!strcmp(name, "decode_occupancy")) g_ctx.opt.decode_occupancy = value;
-    else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
+    apply_option(name, value);
 }
 
 }  // extern "C"

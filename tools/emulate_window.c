@@ -1,0 +1,168 @@
+/* emulate_window.c -- CPU model of the window-parallel fragment compressor (csrc/compress_window.cuh).
+ *
+ * Development aid, not part of the product: it evaluates the *round* algorithm the CUDA kernel runs
+ * (32 positions per round: every lane looks its position up in the table as of the round start,
+ * the real chain is then followed through the window, and a lane whose hash equals an earlier
+ * lane's is never trusted) with plain loops, so that its exactness against the oracle
+ * (oracle/snappy_oracle.c, the restatement of src/internal.jl:127-250) can be checked on a CPU
+ * before the kernel ever runs.   gcc -O2 -o emulate_window tools/emulate_window.c oracle/snappy_oracle.c
+ *
+ * Usage: emulate_window FILE...   -> per file: fragments compared, mismatches, rounds per fragment
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../oracle/snappy_oracle.h"
+
+static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+typedef struct { const uint8_t *F; long n, lim; uint32_t shift; uint16_t T[16384]; uint8_t *out, *op;
+                 long rounds, hops, slow, generic; } Frag;
+
+static uint32_t hashw(const Frag *f, uint32_t w) { return (w * 0x1e35a7bdu) >> f->shift; }
+
+static void emit_literal(Frag *f, long from, long to) {
+    long len = to - from; if (len <= 0) return;
+    uint32_t n = (uint32_t)(len - 1); uint8_t *op = f->op;
+    if (len < 60) *op++ = (uint8_t)(n << 2);
+    else { uint8_t *base = op; int count = 0; while (n > 0) { *++op = (uint8_t)n; n >>= 8; count++; } *base = (uint8_t)((59 + count) << 2); op++; }
+    memcpy(op, f->F + from, (size_t)len); f->op = op + len;
+}
+static uint8_t *copy64(uint8_t *op, uint32_t off, uint32_t len) {
+    if (len < 12 && off < 2048) { *op++ = (uint8_t)(1 + ((len - 4) << 2) + ((off >> 3) & 0xe0)); *op++ = (uint8_t)off; }
+    else { uint32_t u = 2 + ((len - 1) << 2) + (off << 8); *op++ = (uint8_t)u; *op++ = (uint8_t)(u >> 8); *op++ = (uint8_t)(u >> 16); }
+    return op;
+}
+static void emit_copy(Frag *f, uint32_t off, uint32_t len) {
+    uint8_t *op = f->op;
+    if (len >= 12) { while (len >= 68) { op = copy64(op, off, 64); len -= 64; } if (len > 64) { op = copy64(op, off, 60); len -= 60; } }
+    f->op = copy64(op, off, len);
+}
+static void record(Frag *f, long lit_from, long ip, long cand, long M) { emit_literal(f, lit_from, ip); emit_copy(f, (uint32_t)(ip - cand), (uint32_t)M); }
+
+/* probe offsets of the skip heuristic, :162-172 */
+static uint32_t PO[400];
+static void init_po(void) { uint32_t skip = 32, off = 0; PO[0] = 0; for (int i = 1; i < 400; i++) { uint32_t b = skip >> 5; skip += b; off += b; if (off > 0x100000u) off = 0x100000u; PO[i] = off; } }
+
+enum { ARR = 0, SCAN = 1 };
+
+static size_t compress_fragment_window(Frag *f) {
+    const uint8_t *F = f->F; const long n = f->n, lim = n - 16; f->lim = lim; f->op = f->out;
+    memset(f->T, 0, sizeof f->T);
+    long lit_from = 0;
+    if (n >= 15) {
+        int mode = SCAN; long a = 1, scan_s = 1;
+        for (;;) {
+            /* ---- generic scan rounds (probe index >= 32, stride > 1): the old path */
+            if (mode == SCAN && a - scan_s >= 32) {
+                f->generic++;
+                long k = a - scan_s; /* == 32 */
+                long ip = -1, cand = 0; int fin = 0;
+                for (;; k++) {
+                    long p = scan_s + PO[k], pn = scan_s + PO[k + 1];
+                    if (pn > lim) { fin = 1; break; }
+                    uint32_t h = hashw(f, ld32(F + p)); cand = f->T[h]; f->T[h] = (uint16_t)p;
+                    if (ld32(F + cand) == ld32(F + p)) { ip = p; break; }
+                }
+                if (fin) break;
+                long M = 4; while (ip + M < n && F[cand + M] == F[ip + M]) M++;
+                record(f, lit_from, ip, cand, M); ip += M; lit_from = ip;
+                if (ip >= lim) break;
+                mode = ARR; a = ip; continue;
+            }
+            f->rounds++;
+            /* ---- lane evaluation against the table as of the round start */
+            uint32_t H[32], t[32], m[32]; int V[32], dup[32];
+            if (mode == ARR) f->T[hashw(f, ld32(F + a - 1))] = (uint16_t)(a - 1); /* :233 */
+            for (int l = 0; l < 32; l++) {
+                long q = a + l; V[l] = q < lim;
+                H[l] = V[l] ? hashw(f, ld32(F + q)) : (0x80000000u | (uint32_t)l);
+                t[l] = V[l] ? f->T[H[l]] : 0; dup[l] = 0;
+                for (int j = 0; j < l; j++) if (H[j] == H[l]) dup[l] = 1;
+                uint32_t k = 0; if (V[l]) while (k < 16 && F[t[l] + k] == F[q + k]) k++;
+                m[l] = k;
+            }
+            uint32_t ins = 0; int fin = 0, next_mode = -1; long next_a = 0;
+            long slow_ip = -1, slow_cand = 0;
+            int l = 0; int scanning = (mode == SCAN);
+            for (;;) {
+                f->hops++;
+                if (!scanning) { /* arrival at lane l: :228-238 */
+                    if (l > 0 && dup[l]) { next_mode = ARR; next_a = a + l; break; }
+                    if (l > 0) ins |= 1u << (l - 1);
+                    ins |= 1u << l;
+                    if (m[l] >= 4) {
+                        if (m[l] == 16) { slow_ip = a + l; slow_cand = t[l]; break; }
+                        record(f, lit_from, a + l, t[l], m[l]); lit_from = a + l + m[l];
+                        long tgt = l + m[l];
+                        if (a + tgt >= lim) { fin = 1; break; }
+                        if (tgt >= 32) { next_mode = ARR; next_a = a + tgt; break; }
+                        l = (int)tgt; continue;
+                    }
+                    scanning = 1; scan_s = a + l + 1; l = l + 1; continue;
+                }
+                /* scanning from lane l: :167-194 */
+                int e = l;
+                for (; e < 32; e++) {
+                    if (!V[e]) break;
+                    if (a + e - scan_s >= 32) break;
+                    if (dup[e] && e > 0) break;
+                    if (m[e] >= 4) break;
+                    ins |= 1u << e;
+                }
+                if (e >= 32) { next_mode = SCAN; next_a = a + 32; break; }
+                if (!V[e]) { fin = 1; break; }
+                if (a + e - scan_s >= 32) { next_mode = SCAN; next_a = a + e; break; }
+                if (dup[e] && e > 0) { next_mode = SCAN; next_a = a + e; break; }
+                ins |= 1u << e; /* hit */
+                if (m[e] == 16) { slow_ip = a + e; slow_cand = t[e]; break; }
+                record(f, lit_from, a + e, t[e], m[e]); lit_from = a + e + m[e];
+                long tgt = e + m[e];
+                if (a + tgt >= lim) { fin = 1; break; }
+                if (tgt >= 32) { next_mode = ARR; next_a = a + tgt; break; }
+                scanning = 0; l = (int)tgt;
+            }
+            /* ---- commit the inserts of the path; on equal hashes the later position wins (:191) */
+            for (int k = 0; k < 32; k++) if (ins >> k & 1) f->T[hashw(f, ld32(F + a + k))] = (uint16_t)(a + k);
+            if (slow_ip >= 0) { /* long copy: full-length compare */
+                f->slow++;
+                long M = 16; while (slow_ip + M < n && F[slow_cand + M] == F[slow_ip + M]) M++;
+                record(f, lit_from, slow_ip, slow_cand, M); lit_from = slow_ip + M;
+                if (lit_from >= lim) break;
+                mode = ARR; a = lit_from; continue;
+            }
+            if (fin) break;
+            mode = next_mode; a = next_a;
+        }
+    }
+    if (lit_from < n) emit_literal(f, lit_from, n);
+    return (size_t)(f->op - f->out);
+}
+
+int main(int argc, char **argv) {
+    init_po();
+    for (int ai = 1; ai < argc; ai++) {
+        FILE *fp = fopen(argv[ai], "rb"); if (!fp) { perror(argv[ai]); return 1; }
+        fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+        uint8_t *buf = calloc((size_t)sz + 256, 1); if (fread(buf, 1, (size_t)sz, fp) != (size_t)sz) return 1; fclose(fp);
+        uint32_t entries = sjo_hashtable_entries((uint64_t)sz);
+        uint32_t shift = 32; for (uint32_t e = entries; e > 1; e >>= 1) shift--;
+        long nfrag = (sz + 65535) / 65536, bad = 0; Frag *f = calloc(1, sizeof(Frag)); f->shift = shift;
+        uint8_t *o1 = malloc(80000), *o2 = malloc(80000); uint16_t *tab = malloc(16384 * 2);
+        for (long fr = 0; fr < nfrag; fr++) {
+            long n = sz - fr * 65536 < 65536 ? sz - fr * 65536 : 65536;
+            /* the kernel reads past the fragment end only into readable memory; values there must not matter */
+            uint8_t *frag = calloc((size_t)n + 256, 1); memcpy(frag, buf + fr * 65536, (size_t)n); memset(frag + n, 0xA5, 200);
+            f->F = frag; f->n = n; f->out = o1;
+            size_t c1 = compress_fragment_window(f);
+            memset(tab, 0xff, entries * 2);
+            size_t c2 = sjo_compress_fragment(frag, (size_t)n, o2, tab, entries);
+            if (c1 != c2 || memcmp(o1, o2, c1)) { bad++; if (bad < 4) fprintf(stderr, "%s: fragment %ld differs (%zu vs %zu)\n", argv[ai], fr, c1, c2); }
+            free(frag);
+        }
+        printf("%s: %ld fragments, %ld mismatches, rounds/frag %.0f hops/round %.2f slow/frag %.0f generic/frag %.0f\n", argv[ai], nfrag, bad,
+               (double)f->rounds / nfrag, (double)f->hops / (f->rounds ? f->rounds : 1), (double)f->slow / nfrag, (double)f->generic / nfrag);
+    }
+    return 0;
+}

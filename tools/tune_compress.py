@@ -10,6 +10,9 @@ nfrag = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 raw = synth.mix(nfrag, seed=2026)
 d = torch.from_numpy(raw).cuda()
 ref = None
+for kv in sys.argv[3:]:  # global library options, e.g. window=1
+    k_, v_ = kv.split('=')
+    device.set_option(k_, int(v_))
 for cfg in (sys.argv[2] if len(sys.argv) > 2 else '6,0,2;6,14,2').split(';'):
     v = [int(x) for x in cfg.split(',')]
     sm, l2, rs = v[:3]
