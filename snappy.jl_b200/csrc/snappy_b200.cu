@@ -17,6 +17,7 @@
 #include "compress.cuh"
 #include "compress_chain.cuh"
 #include "compress_window.cuh"
+#include "compress_wide.cuh"
 #include "decompress.cuh"
 #include "parse.cuh"
 
@@ -54,6 +55,7 @@ struct Options {
     int compress_variant = 0;   // 0 = lane-speculative chain kernel, 1 = serial smem kernel, 2 = ring kernel
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
     int l2_reserve = 1;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
+    int wide = 0;               // 2 or 4: warps per fragment of the wide window kernel (compress_wide.cuh); 0 = off
     int window = 1;             // 1 = window-parallel kernel (compress_window.cuh), 0 = step-wise chain kernel
     int ring_smem = 2048;       // history ring per shared-table warp (bytes, power of two >= 1024)
     int ring_l2 = 1024;         // history ring per global-table warp
@@ -121,6 +123,7 @@ void apply_option(const char* name, int value) {
         (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
     }
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
+    else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
     else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
     else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
@@ -170,6 +173,8 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // both kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
     // CTAs fit next to the shared-table CTA
+    CU(cudaFuncSetAttribute(k_compress_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -293,6 +298,19 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     const u32 ctas_b = (wb && (nfrag > warps_a + reserve || !wa)) ? (u32)(c.sm_count * c.opt.l2_ctas) : 0u;
     if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * kMaxTableEntries * 2));
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
+    if (c.opt.wide == 2 || c.opt.wide == 4) {  // kW warps per fragment, shared tables only
+        const u32 chains = (u32)c.opt.smem_chains, ra = (u32)c.opt.ring_smem;
+        u32 ctas = (nfrag + chains - 1) / chains;
+        if (ctas > (u32)c.sm_count) ctas = (u32)c.sm_count;
+        if (c.opt.wide == 4)
+            k_compress_wide<4><<<ctas, chains * 128, (size_t)chains * (kMaxTableEntries * 2 + ra + sizeof(WideCtl<4>)), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, descs, ndesc, ra);
+        else
+            k_compress_wide<2><<<ctas, chains * 64, (size_t)chains * (kMaxTableEntries * 2 + ra + sizeof(WideCtl<2>)), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, descs, ndesc, ra);
+        *launches += 1;
+        return SNAPPY_B200_OK;
+    }
     const bool window = c.opt.window != 0;
     const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
     if (ctas_a) {

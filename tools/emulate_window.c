@@ -140,8 +140,119 @@ static size_t compress_fragment_window(Frag *f) {
     return (size_t)(f->op - f->out);
 }
 
+
+/* ---- W windows of 32 positions per round (compress_window.cuh, multi-warp form): all windows are
+ * evaluated against the table as of the round start; the chain then passes through them in order,
+ * the inserts of window k being committed before window k+1 is entered; a lane of window k+1 is
+ * trusted iff the table still holds the value it looked up and no lower lane of ITS window has its hash. */
+static int WW = 4;
+static long st_windows, st_stale_lanes, st_entered;
+static size_t compress_fragment_multi(Frag *f) {
+    const uint8_t *F = f->F; const long n = f->n, lim = n - 16; f->lim = lim; f->op = f->out;
+    memset(f->T, 0, sizeof f->T);
+    long lit_from = 0;
+    if (n >= 15) {
+        int mode = SCAN; long a = 1, scan_s = 1;
+        for (;;) {
+            if (mode == SCAN && a - scan_s >= 32) {
+                f->generic++;
+                long k = a - scan_s; long ip = -1, cand = 0; int fin = 0;
+                for (;; k++) {
+                    long p = scan_s + PO[k], pn = scan_s + PO[k + 1];
+                    if (pn > lim) { fin = 1; break; }
+                    uint32_t h = hashw(f, ld32(F + p)); cand = f->T[h]; f->T[h] = (uint16_t)p;
+                    if (ld32(F + cand) == ld32(F + p)) { ip = p; break; }
+                }
+                if (fin) break;
+                long M = 4; while (ip + M < n && F[cand + M] == F[ip + M]) M++;
+                record(f, lit_from, ip, cand, M); ip += M; lit_from = ip;
+                if (ip >= lim) break;
+                mode = ARR; a = ip; continue;
+            }
+            f->rounds++;
+            if (mode == ARR) f->T[hashw(f, ld32(F + a - 1))] = (uint16_t)(a - 1);
+            /* parallel evaluation of W windows against the table as of now */
+            static uint32_t H[8][32], t[8][32], m[8][32]; static int V[8][32], dup[8][32];
+            for (int w = 0; w < WW; w++) for (int l = 0; l < 32; l++) {
+                long q = a + 32 * w + l; V[w][l] = q < lim;
+                H[w][l] = V[w][l] ? hashw(f, ld32(F + q)) : (0x80000000u | (uint32_t)l);
+                t[w][l] = V[w][l] ? f->T[H[w][l]] : 0; dup[w][l] = 0;
+                for (int j = 0; j < l; j++) if (H[w][j] == H[w][l]) dup[w][l] = 1;
+                uint32_t k = 0; if (V[w][l]) while (k < 16 && F[t[w][l] + k] == F[q + k]) k++;
+                m[w][l] = k;
+            }
+            int fin = 0, done = 0; long slow_ip = -1, slow_cand = 0;
+            long cur = a;            /* absolute position of the pending arrival / next scan probe */
+            int scanning = (mode == SCAN);
+            for (int w = 0; w < WW && !done; w++) {
+                long base = a + 32 * w;
+                if (cur >= base + 32) continue;          /* the chain jumped over this window */
+                st_entered++;
+                uint32_t ins = 0; int l = (int)(cur - base);
+                /* :233 an arrival at lane 0 of a later window: the position before it lies in the previous window */
+                if (!scanning && l == 0 && w > 0) f->T[hashw(f, ld32(F + base - 1))] = (uint16_t)(base - 1);
+                /* validation: the table must still hold what the lane looked up */
+                int stale[32];
+                for (int l = 0; l < 32; l++) { stale[l] = V[w][l] && w > 0 && f->T[H[w][l]] != t[w][l]; st_stale_lanes += stale[l]; }
+                st_windows++;
+                for (;;) {
+                    f->hops++;
+                    if (!scanning) {
+                        int untrusted = (l > 0 && dup[w][l]) || stale[l];
+                        if (untrusted && !(w == 0 && l == 0)) { mode = ARR; cur = base + l; done = 1; break; }
+                        /* :233 position before the arrival */
+                        if (l > 0) ins |= 1u << (l - 1);
+                        ins |= 1u << l;
+                        if (m[w][l] >= 4) {
+                            if (m[w][l] == 16) { slow_ip = base + l; slow_cand = t[w][l]; done = 1; break; }
+                            record(f, lit_from, base + l, t[w][l], m[w][l]); lit_from = base + l + m[w][l];
+                            long tgt = l + m[w][l];
+                            if (base + tgt >= lim) { fin = 1; done = 1; break; }
+                            if (tgt >= 32) { mode = ARR; scanning = 0; cur = base + tgt; break; }
+                            l = (int)tgt; continue;
+                        }
+                        scanning = 1; scan_s = base + l + 1; l = l + 1; continue;
+                    }
+                    int e = l;
+                    for (; e < 32; e++) {
+                        if (!V[w][e]) break;
+                        if (base + e - scan_s >= 32) break;
+                        if ((dup[w][e] && e > 0) || stale[e]) break;
+                        if (m[w][e] >= 4) break;
+                        ins |= 1u << e;
+                    }
+                    if (e >= 32) { mode = SCAN; cur = base + 32; break; }
+                    if (!V[w][e]) { fin = 1; done = 1; break; }
+                    if (base + e - scan_s >= 32) { mode = SCAN; cur = base + e; done = 1; break; }
+                    if ((dup[w][e] && e > 0) || stale[e]) { mode = SCAN; cur = base + e; done = 1; break; }
+                    ins |= 1u << e;
+                    if (m[w][e] == 16) { slow_ip = base + e; slow_cand = t[w][e]; done = 1; break; }
+                    record(f, lit_from, base + e, t[w][e], m[w][e]); lit_from = base + e + m[w][e];
+                    long tgt = e + m[w][e];
+                    if (base + tgt >= lim) { fin = 1; done = 1; break; }
+                    if (tgt >= 32) { mode = ARR; scanning = 0; cur = base + tgt; break; }
+                    scanning = 0; l = (int)tgt;
+                }
+                for (int k = 0; k < 32; k++) if (ins >> k & 1) f->T[H[w][k]] = (uint16_t)(base + k);
+            }
+            if (slow_ip >= 0) {
+                f->slow++;
+                long M = 16; while (slow_ip + M < n && F[slow_cand + M] == F[slow_ip + M]) M++;
+                record(f, lit_from, slow_ip, slow_cand, M); lit_from = slow_ip + M;
+                if (lit_from >= lim) break;
+                mode = ARR; a = lit_from; continue;
+            }
+            if (fin) break;
+            a = cur;   /* mode set above */
+        }
+    }
+    if (lit_from < n) emit_literal(f, lit_from, n);
+    return (size_t)(f->op - f->out);
+}
+
 int main(int argc, char **argv) {
     init_po();
+    if (getenv("WW")) WW = atoi(getenv("WW"));
     for (int ai = 1; ai < argc; ai++) {
         FILE *fp = fopen(argv[ai], "rb"); if (!fp) { perror(argv[ai]); return 1; }
         fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
@@ -155,14 +266,14 @@ int main(int argc, char **argv) {
             /* the kernel reads past the fragment end only into readable memory; values there must not matter */
             uint8_t *frag = calloc((size_t)n + 256, 1); memcpy(frag, buf + fr * 65536, (size_t)n); memset(frag + n, 0xA5, 200);
             f->F = frag; f->n = n; f->out = o1;
-            size_t c1 = compress_fragment_window(f);
+            size_t c1 = getenv("WW") ? compress_fragment_multi(f) : compress_fragment_window(f);
             memset(tab, 0xff, entries * 2);
             size_t c2 = sjo_compress_fragment(frag, (size_t)n, o2, tab, entries);
             if (c1 != c2 || memcmp(o1, o2, c1)) { bad++; if (bad < 4) fprintf(stderr, "%s: fragment %ld differs (%zu vs %zu)\n", argv[ai], fr, c1, c2); }
             free(frag);
         }
-        printf("%s: %ld fragments, %ld mismatches, rounds/frag %.0f hops/round %.2f slow/frag %.0f generic/frag %.0f\n", argv[ai], nfrag, bad,
-               (double)f->rounds / nfrag, (double)f->hops / (f->rounds ? f->rounds : 1), (double)f->slow / nfrag, (double)f->generic / nfrag);
+        printf("%s: %ld fragments, %ld mismatches, rounds/frag %.0f hops/round %.2f slow/frag %.0f generic/frag %.0f windows entered/round %.2f stale lanes/window %.2f\n", argv[ai], nfrag, bad,
+               (double)f->rounds / nfrag, (double)f->hops / (f->rounds ? f->rounds : 1), (double)f->slow / nfrag, (double)f->generic / nfrag, (double)st_entered / (f->rounds ? f->rounds : 1), (double)st_stale_lanes / (st_windows ? st_windows : 1)); st_entered = st_windows = st_stale_lanes = 0;
     }
     return 0;
 }
