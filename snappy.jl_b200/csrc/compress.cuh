@@ -705,6 +705,54 @@ k_scan_sizes(const u32* __restrict__ sizes, u32 nfrag, u64 base, u64* __restrict
     }
 }
 
+// K2s: the scan of one chunk of the streamed host-buffer path.  Waits until all `need` fragments of
+// the chunk have been compressed (done counter of k_compress_window), then scans <= 1024 sizes behind
+// the running stream length.  256 threads so that it fits next to the persistent compress CTAs.
+__global__ void __launch_bounds__(256)
+k_scan_chunk(const u32* __restrict__ sizes, u32 nf, u64* __restrict__ offsets, u64* __restrict__ running,
+             const u32* done, u32 need) {
+    __shared__ u64 warp_excl[8];
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        while (*reinterpret_cast<const volatile u32*>(done) < need) __nanosleep(1000);
+        __threadfence();
+    }
+    __syncthreads();
+    u64 v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = (tid * 4 + k < nf) ? __ldcg(sizes + tid * 4 + k) : 0;
+        s += v[k];
+    }
+    u64 incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= (u32)d) incl += t;
+    }
+    if (lane == 31) warp_excl[wid] = incl;
+    __syncthreads();
+    u64 before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        if ((u32)w < wid) before += warp_excl[w];
+        total += warp_excl[w];
+    }
+    const u64 base = *running;
+    u64 ex = base + before + (incl - s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (tid * 4 + k < nf) offsets[tid * 4 + k] = ex;
+        ex += v[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        offsets[nf] = base + total;
+        *running = base + total;
+    }
+}
+
+
 // K3: concatenate the per-fragment scratch slots into the contiguous stream.  One CTA per
 // fragment; destination-aligned 16-byte stores, source read as aligned words + funnel shift.
 __global__ void __launch_bounds__(256)

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kSmemTable ? 224 : 448, kSmemTable ? 1 : 2)
 k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                   const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
                   u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
-                  const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes) {
+                  const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes,
+                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarp = blockDim.x >> 5;
@@ -338,6 +339,14 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         if (lane == 0) frag = atomicAdd(counter, 1u);
         frag = __shfl_sync(kFullMask, frag, 0);
         if (frag >= nfrag) break;
+        if (ready) {  // streamed input (host-buffer API): wait until this fragment and the one behind it
+                      // (the kernel reads a few bytes past a fragment's end) have landed
+            if (lane == 0) {
+                const u32 need = frag + 2u < nfrag ? frag + 2u : nfrag;
+                while (*reinterpret_cast<const volatile u32*>(ready) < need) __nanosleep(500);
+            }
+            __syncwarp();
+        }
         const u8* sbase = g_in;
         const u8* stail = tail_copy;
         u64 slen = shard_len;
@@ -374,6 +383,11 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
         ch.run_window();
         if (lane == 0) frag_sizes[frag] = ch.op;
+        if (done) {  // streamed output: per-chunk completion counts release the compaction of a chunk
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(done + frag / done_div, 1u);
+        }
         __syncwarp();
     }
 }

@@ -76,9 +76,9 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     // scratch for compress
-    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs;
+    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;  // host-buffer API pipeline
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr, s_pack = nullptr;  // host-buffer API pipeline
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for decode
@@ -191,6 +191,7 @@ int ctx_init_locked(int device) {
     CU(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_pack, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxPipeChunks; i++) {
         CU(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
@@ -278,11 +279,19 @@ int stage_tail(Context& c, const u8* d_in, size_t len, size_t slot, cudaStream_t
 
 // descs == nullptr: the fragments of d_in[0 .. len); else `nfrag_total` fragments described by the
 // device array descs[ndesc] (tails already staged).
+// streamed host-buffer path: the kernels wait for `ready` (fragments resident) and count finished
+// fragments per chunk of `div` fragments in `done`; the caller stages the tail itself
+struct Gate {
+    const u32* ready = nullptr;
+    u32* done = nullptr;
+    u32 div = 1;
+};
+
 int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* scratch, u32* sizes,
                          cudaStream_t st, int* launches, const ShardDesc* descs = nullptr, u32 ndesc = 0,
-                         u32 nfrag_total = 0) {
+                         u32 nfrag_total = 0, const Gate* gate = nullptr) {
     const u32 nfrag = descs ? nfrag_total : (u32)((len + kBlockSize - 1) / kBlockSize);
-    if (!descs) {
+    if (!descs && !gate) {
         CU(c.tail.ensure(kTailSlot));
         int rc = stage_tail(c, d_in, len, 0, st);
         if (rc != SNAPPY_B200_OK) return rc;
@@ -317,7 +326,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         if (window)
             k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra);
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
         else
             k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
@@ -329,7 +338,8 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         if (window)
             k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * rb, c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
-                reserve, descs, ndesc, rb);
+                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
+                gate ? gate->div : 1u);
         else
             k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
@@ -701,6 +711,100 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
                                     (cudaStream_t)stream);
 }
 
+// Host-buffer compress, streamed: ONE launch of the persistent compress kernels
+// covers the whole input.  The input goes up in chunks on a copy stream, each followed by a 4-byte
+// copy that raises the device-side `ready` count the kernels wait on before they touch a fragment;
+// finished fragments are counted per output chunk, and a small scan kernel per chunk waits for its
+// count, after which the chunk is compacted behind the stream so far and its bytes go down on a
+// third stream while the rest still compresses.  Only the running stream length (8 bytes per chunk)
+// is read by the host.
+int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* out_len) {
+    const size_t cf = 1024;  // fragments per chunk (64 MiB up, ~30 MB down)
+    const size_t need = snappy_b200_max_compressed_length(n);
+    const u32 nfrag = (u32)((n + kBlockSize - 1) / kBlockSize);
+    const int nchunks = (int)((nfrag + cf - 1) / cf);
+    CU(c.stage_in.ensure(n + 16));
+    CU(c.stage_out.ensure(need + 16));
+    CU(c.scratch.ensure((size_t)nfrag * kSlotStride));
+    CU(c.frag_sizes.ensure((size_t)nfrag * sizeof(u32)));
+    CU(c.frag_offsets.ensure(((size_t)nfrag + 1) * sizeof(u64) + 8));
+    CU(c.flags.ensure(64 + (size_t)kMaxPipeChunks * 4));
+    CU(c.tail.ensure(kTailSlot));
+    u8* d_in = (u8*)c.stage_in.p;
+    u8* d_out = (u8*)c.stage_out.p;
+    u8* scratch = (u8*)c.scratch.p;
+    u32* sizes = (u32*)c.frag_sizes.p;
+    u64* offs = (u64*)c.frag_offsets.p;
+    u64* running = offs + nfrag + 1;            // device: bytes in the stream so far
+    u32* d_ready = (u32*)c.flags.p;             // device: fragments resident
+    u32* d_done = (u32*)((u8*)c.flags.p + 64);  // device: fragments finished, per chunk
+    u64* h_tot = (u64*)((u8*)c.pinned + 2048);  // host: stream length after each chunk
+    u32* h_ready = (u32*)((u8*)c.pinned + 2048 + kMaxPipeChunks * 8);
+    const u32 shift = table_shift(n);
+    u8* hdr = (u8*)c.pinned + 64;
+    const int k = encode_varint((u32)n, hdr);   // src/Snappy.jl:26
+    u64* h_k = (u64*)((u8*)c.pinned + 96);
+    *h_k = (u64)k;
+    CU(cudaMemsetAsync(c.flags.p, 0, 64 + (size_t)nchunks * 4, c.s_comp));
+    CU(cudaMemcpyAsync(d_out, hdr, (size_t)k, cudaMemcpyHostToDevice, c.s_comp));
+    CU(cudaMemcpyAsync(running, h_k, 8, cudaMemcpyHostToDevice, c.s_comp));
+    CU(cudaEventRecord(c.ev_in[0], c.s_comp));
+    // The copies are enqueued BEFORE the kernels that wait for them: streams can share a hardware queue
+    // (CUDA_DEVICE_MAX_CONNECTIONS), and a copy queued behind a kernel that waits for it would never run.
+    // input: chunk, then the count of resident fragments (the tail copy goes in before the last count)
+    CU(cudaStreamWaitEvent(c.s_h2d, c.ev_in[0], 0));
+    for (int i = 0; i < nchunks; i++) {
+        const size_t off = (size_t)i * cf * kBlockSize;
+        const size_t len = (n - off < cf * kBlockSize) ? (n - off) : cf * kBlockSize;
+        CU(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c.s_h2d));
+        if (i == nchunks - 1) {
+            int rc = stage_tail(c, d_in, n, 0, c.s_h2d);
+            if (rc != SNAPPY_B200_OK) return rc;
+        }
+        h_ready[i] = (i == nchunks - 1) ? nfrag : (u32)((size_t)(i + 1) * cf);
+        CU(cudaMemcpyAsync(d_ready, h_ready + i, 4, cudaMemcpyHostToDevice, c.s_h2d));
+    }
+    // the persistent kernels
+    int launches = 0;
+    Gate gate;
+    gate.ready = d_ready;
+    gate.done = d_done;
+    gate.div = (u32)cf;
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[0], c.s_comp));
+    int rc = launch_chain_kernels(c, d_in, n, shift, scratch, sizes, c.s_comp, &launches, nullptr, 0, 0, &gate);
+    if (rc != SNAPPY_B200_OK) return rc;
+    if (c.opt.timing) {
+        CU(cudaEventRecord(c.ev[1], c.s_comp));
+        c.ev_pending[0] = true;
+    }
+    // output: per chunk wait + scan, compaction, stream length
+    CU(cudaStreamWaitEvent(c.s_pack, c.ev_in[0], 0));
+    for (int i = 0; i < nchunks; i++) {
+        const size_t f0 = (size_t)i * cf;
+        const u32 nf = (u32)((nfrag - f0 < cf) ? (nfrag - f0) : cf);
+        k_scan_chunk<<<1, 256, 0, c.s_pack>>>(sizes + f0, nf, offs + f0, running, d_done + i, nf);
+        k_compact<<<nf, 256, 0, c.s_pack>>>(scratch + f0 * kSlotStride, sizes + f0, offs + f0, d_out);
+        launches += 2;
+        CU(cudaMemcpyAsync(h_tot + i, running, 8, cudaMemcpyDeviceToHost, c.s_pack));
+        CU(cudaEventRecord(c.ev_done[i], c.s_pack));
+    }
+    CU(cudaGetLastError());
+    u64 prev = 0;
+    for (int i = 0; i < nchunks; i++) {
+        CU(cudaEventSynchronize(c.ev_done[i]));
+        const u64 end = h_tot[i];
+        CU(cudaMemcpyAsync(out + prev, d_out + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, c.s_d2h));
+        prev = end;
+    }
+    CU(cudaStreamSynchronize(c.s_d2h));
+    CU(cudaStreamSynchronize(c.s_comp));
+    CU(cudaStreamSynchronize(c.s_h2d));
+    harvest_timing(c, 0);
+    c.last_launches[0] = launches;
+    *out_len = (size_t)prev;
+    return SNAPPY_B200_OK;
+}
+
 // Host-buffer compress, pipelined: the input goes up in chunks of
 // kPipeChunkFrags fragments on a copy stream, each chunk is compressed + compacted behind the
 // previous one's bytes as soon as it has landed, and its bytes go back down on a third stream
@@ -773,6 +877,9 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
     Context& c = g_ctx;
+    if (c.opt.compress_variant == 0 && c.opt.host_pipeline == 1 && c.opt.window && !c.opt.wide &&
+        n > (size_t)2048 * kBlockSize)
+        return compress_host_streamed(c, in, n, out, out_len);
     if (c.opt.compress_variant == 0 && c.opt.host_pipeline && n > (size_t)c.opt.pipe_chunk_frags * kBlockSize)
         return compress_host_pipelined(c, in, n, out, out_len);
     CU(c.stage_in.ensure(n + 16));

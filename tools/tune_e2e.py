@@ -1,4 +1,5 @@
-"""GPU: host-buffer API (e2e) timing vs pipeline chunk size."""
+"""GPU: host-buffer API (e2e) timing for different library options, e.g.
+    python tools/tune_e2e.py host_pipeline=1 host_pipeline=2,pipe_chunk_frags=4096"""
 import sys, os, time, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,8 +15,11 @@ h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
 h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
 lib = Snappy._abi.lib()
 lib.snappy_b200_init(0)
-for chunk in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "4096,2048,8192,1024").split(",")]:
-    device.set_option("pipe_chunk_frags", chunk)
+for cfg in (sys.argv[1:] or ["host_pipeline=1"]):  # each argument: comma-separated name=value options
+    for kv in cfg.split(","):
+        k_, v_ = kv.split("=")
+        device.set_option(k_, int(v_))
+    chunk = cfg
     for rep in range(3):
         ol = ctypes.c_size_t(cap)
         t0 = time.perf_counter()
@@ -25,5 +29,5 @@ for chunk in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "4096,2048,
         rc2 = lib.snappy_b200_uncompress(h_out.data_ptr(), ol.value, h_back.data_ptr(), ctypes.byref(bl))
         t2 = time.perf_counter()
     ok = rc == 0 and rc2 == 0 and bool(torch.equal(h_back, host_in))
-    print("chunk=%d compress %.1f ms uncompress %.1f ms total %.1f ms -> %.1f GB/s ok=%s" % (
+    print("%s: compress %.1f ms uncompress %.1f ms total %.1f ms -> %.1f GB/s ok=%s" % (
         chunk, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t2 - t0) * 1e3, n / (t2 - t0) / 1e9, ok), flush=True)
