@@ -710,7 +710,7 @@ k_scan_sizes(const u32* __restrict__ sizes, u32 nfrag, u64 base, u64* __restrict
 // the running stream length.  256 threads so that it fits next to the persistent compress CTAs.
 __global__ void __launch_bounds__(256)
 k_scan_chunk(const u32* __restrict__ sizes, u32 nf, u64* __restrict__ offsets, u64* __restrict__ running,
-             const u32* done, u32 need) {
+             const u32* done, u32 need, u64* host_total) {
     __shared__ u64 warp_excl[8];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -749,6 +749,10 @@ k_scan_chunk(const u32* __restrict__ sizes, u32 nf, u64* __restrict__ offsets, u
     if (tid == 0) {
         offsets[nf] = base + total;
         *running = base + total;
+        // the stream length so far goes straight into pinned host memory (a device-to-host copy would
+        // queue behind the output copies on the copy engine)
+        *host_total = base + total;
+        __threadfence_system();
     }
 }
 

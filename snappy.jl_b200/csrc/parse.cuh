@@ -24,6 +24,11 @@
 //                     anomaly flags.  A scan gives output offsets, k_build_index records the
 //                     compressed position of every 64 KiB output boundary.
 //
+// Segments (streamed host-buffer uncompress): the same passes run over a SEGMENT [hdr, E) of the
+// stream whose first byte is a known element start (hdr) and whose elements may run past E (L stays
+// the true end of the stream): a chain that leaves the segment ends at the first element start
+// >= E, which is reported (counters64[1]) and becomes the next segment's hdr.
+//
 // If the stream is "fragment-clean" (no element straddles, no copy reaches across a 64 KiB output
 // boundary -- true for everything Snappy.jl emits) the result is the side index the compressor
 // would have produced and the indexed decoder runs; it re-validates every fragment, so a wrong
@@ -34,7 +39,7 @@
 
 namespace sb200 {
 
-constexpr u32 kParseChunk = 4096;     // compressed bytes per chunk
+constexpr u32 kParseChunkLog2 = 10;   // default: 1 KiB of compressed bytes per chunk (one thread each)
 constexpr u32 kParseLookback = 1024;  // guess walk starts this far before the chunk
 constexpr u32 kParseThreads = 128;
 constexpr u32 kBridgeBudget = 20000;  // elements a bridge may walk before it gives up
@@ -95,17 +100,18 @@ __device__ __forceinline__ bool walk_chunk(const u8* __restrict__ in, u64 L, u64
     return true;
 }
 
-__device__ __forceinline__ void chunk_range(u64 hdr, u64 L, u32 k, u64& start, u64& end) {
-    start = hdr + (u64)k * kParseChunk;
-    end = (start + kParseChunk < L) ? (start + kParseChunk) : L;
+// chunk k of the segment [hdr, E)
+__device__ __forceinline__ void chunk_range(u64 hdr, u64 E, u32 k, u32 pshift, u64& start, u64& end) {
+    start = hdr + ((u64)k << pshift);
+    end = (start + (1ull << pshift) < E) ? (start + (1ull << pshift)) : E;
 }
 
 __global__ void __launch_bounds__(kParseThreads)
-k_parse_guess(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+k_parse_guess(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, u64 E, u32 pshift) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     u64 start, end;
-    chunk_range(hdr, L, k, start, end);
+    chunk_range(hdr, E, k, pshift, start, end);
     u64 ip = hdr;
     Element e;
     if (k > 0) {
@@ -123,15 +129,20 @@ k_parse_guess(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
 }
 
 __global__ void __launch_bounds__(kParseThreads)
-k_parse_bridge(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+k_parse_bridge(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, u64 E, u32 pshift) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     u64 x = pa.exit[k];
     u32 nx = kNextDead, prev = kNextDead;
     Element e;
+    pa.entry[k] = kDeadPos;  // until k_parse_entries: where a chain that leaves the segment through k ends
     for (u32 steps = 0; x != kDeadPos && steps < kBridgeBudget; steps++) {
-        if (x + 1 >= L) { nx = nchunk; break; }  // the chain ends here (a lone trailing byte is ignored)
-        const u32 j = (u32)((x - hdr) / kParseChunk);
+        if (x + 1 >= L || x >= E) {  // the chain ends here (a lone trailing byte is ignored) or leaves the segment
+            nx = nchunk;
+            pa.entry[k] = x;
+            break;
+        }
+        const u32 j = (u32)((x - hdr) >> pshift);
         if (j != prev) {  // x is this chain's first element start in chunk j
             if (pa.first[j] == x) { nx = j; break; }
             prev = j;
@@ -160,10 +171,12 @@ k_parse_reach(u32 nchunk, const u32* __restrict__ nx, u32* __restrict__ nx_out, 
 // bridge enters its real entry.
 __global__ void __launch_bounds__(kParseThreads)
 k_parse_entries(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
-                const u32* __restrict__ next_orig, int phase) {
+                const u32* __restrict__ next_orig, int phase, u64 E, u32 pshift) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     if (phase == 0) {
+        // the reached chunk whose chain leaves the segment reports where (exactly one such chunk)
+        if (pa.reach[k] && next_orig[k] == nchunk) reinterpret_cast<u64*>(pa.counters)[1] = pa.entry[k];
         pa.entry[k] = pa.reach[k] ? pa.first[k] : kDeadPos;
         if (pa.reach[k] && next_orig[k] == kNextDead) atomicOr(&pa.counters[0], PF_BROKEN);
         return;
@@ -173,8 +186,8 @@ k_parse_entries(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArra
     u32 prev = kNextDead;
     Element e;
     for (u32 steps = 0; steps < kBridgeBudget; steps++) {
-        if (x + 1 >= L) break;
-        const u32 j = (u32)((x - hdr) / kParseChunk);
+        if (x + 1 >= L || x >= E) break;
+        const u32 j = (u32)((x - hdr) >> pshift);
         if (j != prev) {
             if (pa.first[j] == x) break;  // joined: phase 0 already set entry[j]
             pa.entry[j] = x;
@@ -185,14 +198,14 @@ k_parse_entries(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArra
 }
 
 __global__ void __launch_bounds__(kParseThreads)
-k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa) {
+k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, u64 E, u32 pshift) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     u64 ip = pa.entry[k];
     u64 produced = 0;
     if (ip != kDeadPos) {
         u64 start, end;
-        chunk_range(hdr, L, k, start, end);
+        chunk_range(hdr, E, k, pshift, start, end);
         if (!walk_chunk(in, L, end, ip, produced) || produced > 0xffffffffull) {
             atomicOr(&pa.counters[0], PF_ANOMALY);
             produced = 0;
@@ -205,15 +218,15 @@ k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
 // element that starts exactly on a 64 KiB output boundary; flag anything not fragment-clean.
 __global__ void __launch_bounds__(kParseThreads)
 k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
-              const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag) {
+              const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag, u64 E, u64 out_base, u32 pshift) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
-    if (k == 0) index[nfrag] = L;
+    if (k == 0 && E >= L) index[nfrag] = L;
     u64 ip = pa.entry[k];
     if (ip == kDeadPos) return;
     u64 start, end;
-    chunk_range(hdr, L, k, start, end);
-    u64 op = out_off[k];
+    chunk_range(hdr, E, k, pshift, start, end);
+    u64 op = out_base + out_off[k];  // out_base: output bytes of the segments before this one
     bool clean = true;
     Element e;
     while (ip < end && ip + 1 < L) {
@@ -226,6 +239,15 @@ k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
         op += e.len;
     }
     if (!clean) atomicOr(&pa.counters[0], PF_NOT_CLEAN);
+}
+
+// flags, segment exit and output bytes straight into pinned host memory: a device-to-host copy would
+// queue behind the output copies of the streamed path on the copy engine
+__global__ void k_parse_report(const u32* __restrict__ counters, const u64* __restrict__ total, u64* host3) {
+    host3[0] = counters[0];
+    host3[1] = reinterpret_cast<const u64*>(counters)[1];
+    host3[2] = *total;
+    __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256)

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -66,6 +67,7 @@ struct Options {
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
     int pipe_chunk_frags = (int)kPipeChunkFragsDefault;  // host-buffer API pipeline granularity
+    int parse_chunk_log2 = (int)kParseChunkLog2;  // index-free parse: log2 of the compressed bytes per thread
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
 };
@@ -122,6 +124,7 @@ void apply_option(const char* name, int value) {
         while (r < value && r < 32768) r <<= 1;
         (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
     }
+    else if (!strcmp(name, "parse_chunk_log2")) g_ctx.opt.parse_chunk_log2 = value < 9 ? 9 : (value > 16 ? 16 : value);
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
     else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
@@ -440,21 +443,17 @@ int decode_exact_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_
 
 // decode with a device-resident index of nfrag+1 offsets; returns OK, or -1 when the fast path
 // declined (caller falls back)
-int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
-                          const u64* d_index, cudaStream_t st, u8* host_out = nullptr,
-                          bool* host_copied = nullptr) {
+// Enqueue the indexed decoder for fragments [fa, fb) on `st`; with host_out, in ranges of
+// pipe_chunk_frags fragments, each followed by its device-to-host copy on the copy stream (*ri counts
+// the events used).  No synchronisation.
+int decode_launch(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed, const u64* d_index,
+                  cudaStream_t st, u32 fa, u32 fb, u8* host_out, int* ri, u32 range = 0) {
     const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
-    if (nfrag == 0) return -1;
     DecodeResult* res = (DecodeResult*)c.result.p;
-    CU(cudaMemsetAsync(res, 0, sizeof(DecodeResult), st));
-    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
-    // host-buffer API: decode in ranges and send each finished range down while the next decodes
-    const size_t kPipeChunkFrags = (size_t)c.opt.pipe_chunk_frags;
-    const bool ranged = host_out && c.opt.host_pipeline && nfrag > kPipeChunkFrags;
-    const u32 step = ranged ? (u32)kPipeChunkFrags : nfrag;
-    int ri = 0;
-    for (u32 f0 = 0; f0 < nfrag; f0 += step, ri++) {
-        const u32 cnt = (nfrag - f0 < step) ? (nfrag - f0) : step;
+    const bool ranged = host_out != nullptr;
+    const u32 step = ranged ? (range ? range : (u32)c.opt.pipe_chunk_frags) : (fb - fa);
+    for (u32 f0 = fa; f0 < fb; f0 += step) {
+        const u32 cnt = (fb - f0 < step) ? (fb - f0) : step;
         const u32 grid = (cnt + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
         if (c.opt.decode_occupancy == 12)
             k_decode_fragments<12><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
@@ -467,14 +466,23 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
                                                                             (u64)n, d_out, (u64)claimed, res);
         c.last_launches[1] += 1;
         if (ranged) {
+            if (*ri >= kMaxPipeChunks) return fail_cuda(cudaErrorInvalidValue, "decode_launch: too many ranges");
             const size_t ob = (size_t)f0 * kBlockSize;
             const size_t ol = ((size_t)claimed - ob < (size_t)cnt * kBlockSize) ? ((size_t)claimed - ob)
                                                                                  : (size_t)cnt * kBlockSize;
-            CU(cudaEventRecord(c.ev_done[ri], st));
-            CU(cudaStreamWaitEvent(c.s_d2h, c.ev_done[ri], 0));
+            CU(cudaEventRecord(c.ev_done[*ri], st));
+            CU(cudaStreamWaitEvent(c.s_d2h, c.ev_done[*ri], 0));
             CU(cudaMemcpyAsync(host_out + ob, d_out + ob, ol, cudaMemcpyDeviceToHost, c.s_d2h));
+            *ri += 1;
         }
     }
+    return SNAPPY_B200_OK;
+}
+
+// Wait for the decoder and read its verdict: OK, or -1 when some fragment was inconsistent with the index.
+int decode_finish(Context& c, cudaStream_t st, bool ranged) {
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    CU(cudaStreamSynchronize(c.s_pack));  // streamed path: the decoder runs there
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[3], st));
         c.ev_pending[1] = true;
@@ -485,20 +493,42 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
     CU(cudaStreamSynchronize(st));
     if (ranged) CU(cudaStreamSynchronize(c.s_d2h));
     harvest_timing(c, 1);
-    if (h->fallback) return -1;
+    return h->fallback ? -1 : SNAPPY_B200_OK;
+}
+
+int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
+                          const u64* d_index, cudaStream_t st, u8* host_out = nullptr,
+                          bool* host_copied = nullptr) {
+    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    if (nfrag == 0) return -1;
+    CU(cudaMemsetAsync(c.result.p, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    // host-buffer API: decode in ranges and send each finished range down while the next decodes
+    const bool ranged = host_out && c.opt.host_pipeline && nfrag > (u32)c.opt.pipe_chunk_frags;
+    int ri = 0;
+    int rc = decode_launch(c, d_in, n, hdr, d_out, claimed, d_index, st, 0, nfrag, ranged ? host_out : nullptr, &ri);
+    if (rc != SNAPPY_B200_OK) return rc;
+    rc = decode_finish(c, st, ranged);
+    if (rc != SNAPPY_B200_OK) return rc;
     if (ranged && host_copied) *host_copied = true;
     return SNAPPY_B200_OK;
 }
 
-// Segmented speculative parse (parse.cuh): build the side index of an arbitrary stream in
-// c.index.  Returns 0 when the index is ready, -1 when the stream is not fragment-clean or shows
-// any anomaly (the exact serial decoder then decides), or a CUDA error status (> 0).
-int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 claimed, cudaStream_t st) {
-    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
-    if (nfrag == 0 || n <= hdr) return -1;
-    const u64 body = n - hdr;
-    if (body / kParseChunk >= 0x7ffffff0ull) return -1;
-    const u32 nchunk = (u32)((body + kParseChunk - 1) / kParseChunk);
+// Segmented speculative parse (parse.cuh) of the segment [hdr, E) of the stream d_in[0 .. n): hdr is
+// an element start, elements may run past E.  Writes the side-index entries of the 64 KiB output
+// boundaries inside the segment into c.index (nfrag + 1 entries for the whole stream), given that
+// the segments before it produced out_base bytes.  *seg_exit = first element start >= E (n at the
+// end of the stream), *seg_out = output bytes of the segment.  Returns 0 when the index entries are
+// ready, -1 when the stream is not fragment-clean or shows any anomaly (the exact serial decoder then
+// decides), or a CUDA error status (> 0).
+int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t E, u64 out_base, u32 nfrag,
+                        cudaStream_t st, u64* seg_exit, u64* seg_out) {
+    if (nfrag == 0 || E <= hdr) return -1;
+    const u64 body = E - hdr;
+    const u32 pshift = (u32)c.opt.parse_chunk_log2;
+    const u64 pchunk = 1ull << pshift;
+    if (body / pchunk >= 0x7ffffff0ull) return -1;
+    const u32 nchunk = (u32)((body + pchunk - 1) / pchunk);
     CU(c.parse_a.ensure(ParseArrays::bytes(nchunk)));
     CU(c.parse_c.ensure(((size_t)nchunk + 1) * 8));  // output offsets
     CU(c.index.ensure(((size_t)nfrag + 1) * 8));
@@ -510,8 +540,8 @@ int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 cla
     CU(cudaMemsetAsync(pa.counters, 0, 64, st));
     const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
     const u32 lgrid = (nchunk + 255) / 256;
-    k_parse_guess<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
-    k_parse_bridge<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
+    k_parse_guess<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
+    k_parse_bridge<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
     c.last_launches[1] += 2;
     // pointer doubling: after r rounds everything within 2^r hops of chunk 0 is marked
     u32* nx = pa.next_a;
@@ -528,29 +558,36 @@ int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 cla
         c.last_launches[1] += 1;
     }
     k_parse_reach<<<lgrid, 256, 0, st>>>(nchunk, nx, nx2, pa.reach);
-    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 0);
-    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 1);
-    k_parse_final<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa);
+    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 0, (u64)E, pshift);
+    k_parse_entries<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, next_orig, 1, (u64)E, pshift);
+    k_parse_final<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
     k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
-    c.last_launches[1] += 5;
+    k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off, (u64*)c.index.p, nfrag,
+                                                  (u64)E, out_base, pshift);
+    c.last_launches[1] += 6;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h + 4, out_off + nchunk, 8, cudaMemcpyDeviceToHost, st));
+    volatile u64* h3 = (volatile u64*)h;
+    k_parse_report<<<1, 1, 0, st>>>(pa.counters, out_off + nchunk, (u64*)h);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
-    u64 total;
-    memcpy(&total, h + 4, 8);
+    const u64 flags = h3[0], ex = h3[1], total = h3[2];
     if (getenv("SNAPPY_B200_DEBUG"))
-        fprintf(stderr, "[snappy_b200] parse: nchunk=%u flags=%u total=%llu claimed=%u\n", nchunk, h[0],
-                (unsigned long long)total, claimed);
-    if (h[0] != 0 || total != claimed) return -1;
-    k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off,
-                                                  (u64*)c.index.p, nfrag);
-    c.last_launches[1] += 1;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h, pa.counters, 16, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (getenv("SNAPPY_B200_DEBUG")) fprintf(stderr, "[snappy_b200] index: flags=%u\n", h[0]);
-    return h[0] ? -1 : 0;
+        fprintf(stderr, "[snappy_b200] parse [%zu, %zu): nchunk=%u flags=%u out=%llu exit=%llu\n", hdr, E, nchunk,
+                (unsigned)flags, (unsigned long long)total, (unsigned long long)ex);
+    if (flags != 0) return -1;
+    *seg_exit = ex;
+    *seg_out = total;
+    return 0;
+}
+
+// The whole stream as one segment.
+int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 claimed, cudaStream_t st) {
+    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    if (nfrag == 0 || n <= hdr) return -1;
+    u64 ex = 0, total = 0;
+    const int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total);
+    if (rc != 0) return rc;
+    return total == claimed ? 0 : -1;
 }
 
 int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
@@ -782,17 +819,16 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
     for (int i = 0; i < nchunks; i++) {
         const size_t f0 = (size_t)i * cf;
         const u32 nf = (u32)((nfrag - f0 < cf) ? (nfrag - f0) : cf);
-        k_scan_chunk<<<1, 256, 0, c.s_pack>>>(sizes + f0, nf, offs + f0, running, d_done + i, nf);
+        k_scan_chunk<<<1, 256, 0, c.s_pack>>>(sizes + f0, nf, offs + f0, running, d_done + i, nf, h_tot + i);
         k_compact<<<nf, 256, 0, c.s_pack>>>(scratch + f0 * kSlotStride, sizes + f0, offs + f0, d_out);
         launches += 2;
-        CU(cudaMemcpyAsync(h_tot + i, running, 8, cudaMemcpyDeviceToHost, c.s_pack));
         CU(cudaEventRecord(c.ev_done[i], c.s_pack));
     }
     CU(cudaGetLastError());
     u64 prev = 0;
     for (int i = 0; i < nchunks; i++) {
         CU(cudaEventSynchronize(c.ev_done[i]));
-        const u64 end = h_tot[i];
+        const u64 end = ((volatile u64*)h_tot)[i];
         CU(cudaMemcpyAsync(out + prev, d_out + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, c.s_d2h));
         prev = end;
     }
@@ -859,7 +895,7 @@ int compress_host_pipelined(Context& c, const u8* in, size_t n, u8* out, size_t*
     u64 prev = 0;
     for (int i = 0; i < nchunks; i++) {
         CU(cudaEventSynchronize(c.ev_done[i]));
-        const u64 end = h_tot[i];
+        const u64 end = ((volatile u64*)h_tot)[i];
         CU(cudaMemcpyAsync(out + prev, d_out + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, c.s_d2h));
         prev = end;
     }
@@ -896,6 +932,87 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
     return SNAPPY_B200_OK;
 }
 
+// Host-buffer uncompress, streamed (SURVEY.md 8(f)1+2): the stream goes up in 16 chunks; it is parsed
+// in 4 segments, each as soon as its bytes (and one chunk of slack for the elements that run past
+// its end) have landed; the fragments a segment completes are decoded and sent down while the next
+// segment is still on its way up.  Returns -1 when the stream needs the whole-stream paths (not
+// fragment-clean, anomalies): the caller then runs them on the resident copy.
+int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32 claimed, u8* out) {
+    const int kChunks = 16, kSegs = 4;
+    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    cudaStream_t st = c.s_comp;
+    u8* d_in = (u8*)c.stage_in.p;
+    u8* d_out = (u8*)c.stage_out.p;
+    CU(c.index.ensure(((size_t)nfrag + 1) * 8));
+    CU(cudaMemsetAsync(c.index.p, 0xff, ((size_t)nfrag + 1) * 8, st));
+    CU(cudaMemsetAsync(c.result.p, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    size_t cb[kChunks + 1];
+    const size_t csz = ((n + kChunks - 1) / kChunks + 4095) & ~(size_t)4095;
+    for (int i = 0; i <= kChunks; i++) cb[i] = ((size_t)i * csz < n) ? (size_t)i * csz : n;
+    for (int i = 0; i < kChunks; i++) {
+        if (cb[i + 1] > cb[i])
+            CU(cudaMemcpyAsync(d_in + cb[i], in + cb[i], cb[i + 1] - cb[i], cudaMemcpyHostToDevice, c.s_h2d));
+        CU(cudaEventRecord(c.ev_in[i], c.s_h2d));
+    }
+    const bool dbg = getenv("SNAPPY_B200_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    u64 entry = hdr, out_base = 0;
+    u64* h_exit = (u64*)((u8*)c.pinned + 1536);  // one slot per segment (read by async copies)
+    u32 f_done = 0;
+    int ri = 0, rc = 0;
+    for (int j = 0; j < kSegs && rc == 0; j++) {
+        const int last_chunk = (j + 1) * (kChunks / kSegs) - 1;            // the segment ends with this chunk
+        const int need_chunk = last_chunk + 1 < kChunks ? last_chunk + 1 : kChunks - 1;  // + slack
+        const size_t E = cb[last_chunk + 1];
+        CU(cudaStreamWaitEvent(st, c.ev_in[need_chunk], 0));
+        if (E <= entry) {  // a long literal swallowed the segment
+            if (j == kSegs - 1) rc = -1;
+            continue;
+        }
+        u64 ex = 0, produced = 0;
+        if (dbg) fprintf(stderr, "[snappy_b200] t=%.2f ms: segment %d parse enqueue\n", ms(), j);
+        rc = build_index_segment(c, d_in, n, (size_t)entry, E, out_base, nfrag, st, &ex, &produced);
+        if (dbg) fprintf(stderr, "[snappy_b200] t=%.2f ms: segment %d parsed rc=%d\n", ms(), j, rc);
+        if (rc != 0) break;
+        out_base += produced;
+        entry = ex;
+        if (out_base > claimed) {
+            rc = -1;
+            break;
+        }
+        u32 f_hi = (j == kSegs - 1) ? nfrag : (u32)(out_base / kBlockSize);
+        if (j < kSegs - 1 && f_hi > f_done && out_base % kBlockSize == 0) {
+            // the boundary element is the next segment's first: its position is this segment's exit
+            h_exit[j] = ex;
+            CU(cudaMemcpyAsync((u64*)c.index.p + f_hi, h_exit + j, 8, cudaMemcpyHostToDevice, st));
+        }
+        if (f_hi > f_done) {
+            // the decoder runs on its own stream, next to the parse of the next segment: one launch per
+            // segment (a launch costs one fragment's latency, ~2.6 ms, however few fragments it has)
+            CU(cudaEventRecord(c.ev_fork, st));
+            CU(cudaStreamWaitEvent(c.s_pack, c.ev_fork, 0));
+            int r2 = decode_launch(c, d_in, n, hdr, d_out, claimed, (const u64*)c.index.p, c.s_pack, f_done, f_hi, out,
+                                   &ri, f_hi - f_done);
+            if (r2 != SNAPPY_B200_OK) return r2;
+            f_done = f_hi;
+        }
+    }
+    if (rc > 0) return rc;
+    if (rc == 0 && out_base != claimed) rc = -1;
+    if (dbg) {
+        CU(cudaStreamSynchronize(st));
+        CU(cudaStreamSynchronize(c.s_pack));
+        fprintf(stderr, "[snappy_b200] t=%.2f ms: decode done\n", ms());
+    }
+    const int rf = decode_finish(c, st, true);
+    if (dbg) fprintf(stderr, "[snappy_b200] t=%.2f ms: copies done\n", ms());
+    CU(cudaStreamSynchronize(c.s_h2d));
+    if (rf > 0) return rf;
+    return (rc == 0 && rf == 0) ? SNAPPY_B200_OK : -1;
+}
+
 int snappy_b200_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_len) {
     if (!out_len || (!in && n)) return SNAPPY_B200_BAD_ARGUMENT;
     u32 claimed = 0;
@@ -909,9 +1026,20 @@ int snappy_b200_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t* ou
     CU(c.stage_in.ensure(n + 16));
     CU(c.stage_out.ensure((size_t)claimed + 16));
     cudaStream_t st = c.s_comp;
-    CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
     size_t olen = 0;
     bool copied = false;
+    bool resident = false;
+    if (c.opt.host_pipeline == 1 && c.opt.decode_variant != 1 && n > ((size_t)64 << 20) && claimed > 0) {
+        c.last_launches[1] = 0;
+        rc = uncompress_host_streamed(c, in, n, hdr, claimed, out);
+        if (rc == SNAPPY_B200_OK) {
+            *out_len = claimed;
+            return SNAPPY_B200_OK;
+        }
+        if (rc > 0) return rc;
+        resident = true;  // the whole-stream paths decide (the stream is on the device by now)
+    }
+    if (!resident) CU(cudaMemcpyAsync(c.stage_in.p, in, n, cudaMemcpyHostToDevice, st));
     rc = uncompress_device_locked(c, (const u8*)c.stage_in.p, n, (u8*)c.stage_out.p, (size_t)claimed,
                                   &olen, nullptr, st, out, &copied);
     if (rc != SNAPPY_B200_OK) return rc;
