@@ -57,6 +57,7 @@ struct Options {
     int smem_chains = 6;        // persistent warps per SM with the table in shared memory
     int l2_reserve = 1;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
     int wide = 0;               // 2 or 4: warps per fragment of the wide window kernel (compress_wide.cuh); 0 = off
+    int l2_persist = 0;         // 1 = pin the global hash tables in L2 (access policy window on the side stream)
     int window = 1;             // 1 = window-parallel kernel (compress_window.cuh), 0 = step-wise chain kernel
     int ring_smem = 2048;       // history ring per shared-table warp (bytes, power of two >= 1024)
     int ring_l2 = 1024;         // history ring per global-table warp
@@ -77,6 +78,7 @@ struct Context {
     bool ready = false;
     int device = -1;
     int sm_count = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;
     // scratch for compress
     DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
@@ -125,6 +127,7 @@ void apply_option(const char* name, int value) {
         (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
     }
     else if (!strcmp(name, "parse_chunk_log2")) g_ctx.opt.parse_chunk_log2 = value < 9 ? 9 : (value > 16 ? 16 : value);
+    else if (!strcmp(name, "l2_persist")) g_ctx.opt.l2_persist = value;
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
     else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
@@ -167,6 +170,13 @@ int ctx_init_locked(int device) {
     }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
+    // L2 persistence for the global hash tables of the global-table compress warps (see launch_chain_kernels)
+    c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (c.l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max);
+    if (getenv("SNAPPY_B200_DEBUG"))
+        fprintf(stderr, "[snappy_b200] L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", prop.l2CacheSize >> 20,
+                c.l2_persist_max >> 20, c.l2_window_max >> 20);
     CU(cudaFuncSetAttribute(k_compress_fragments_serial, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompressSmemBytes));
     CU(cudaFuncSetAttribute(k_compress_pages, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -338,6 +348,20 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     *launches += 1;
     if (ctas_b) {
         CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+        if (c.opt.l2_persist && c.l2_persist_max && c.l2_window_max) {
+            // keep the global hash tables resident in L2: they are the randomly read-and-written state, the
+            // fragment bytes stream through the rest of the cache
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            size_t bytes = (size_t)ctas_b * wb * kMaxTableEntries * 2;
+            if (bytes > c.l2_window_max) bytes = c.l2_window_max;
+            av.accessPolicyWindow.base_ptr = c.gtables.p;
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = bytes <= c.l2_persist_max ? 1.0f : (float)c.l2_persist_max / (float)bytes;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CU(cudaStreamSetAttribute(c.side, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         if (window)
             k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * rb, c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,

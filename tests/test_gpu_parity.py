@@ -295,3 +295,31 @@ def test_batched_shard_api(dev, oracle):
     outs = dev.uncompress_shards_device(datas, fos, lens)
     for o, w, (a, b) in zip(outs, which, cuts):
         assert np.array_equal(o.cpu().numpy(), streams[w][a:b])
+
+
+@pytest.mark.parametrize("options", [
+    {"window": 0},                       # step-wise chain kernel (compress_chain.cuh)
+    {"window": 1, "l2_chains": 0},       # window kernel, shared-memory tables only
+    {"window": 1, "smem_chains": 0},     # window kernel, global tables only
+    {"window": 1, "wide": 4},            # 4 warps per fragment (compress_wide.cuh)
+    {"window": 1, "wide": 2},
+])
+def test_compress_kernel_variants_bit_exact(dev, oracle, options):
+    """every compress kernel in the library produces the oracle's bytes (the default is the window
+    kernel with both table placements running side by side)"""
+    import torch
+    from snappy_jl_b200 import synth
+    defaults = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6}
+    raw = np.concatenate([synth.mix(96, seed=5, tail=777),
+                          np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
+                                        dtype=np.uint8)])
+    want = oracle.compress_np(raw)
+    try:
+        for k, v in options.items():
+            dev.set_option(k, v)
+        stream, _ = dev.compress_device(to_dev(raw), want_index=False)
+        got = stream.cpu().numpy()
+    finally:
+        for k, v in defaults.items():
+            dev.set_option(k, v)
+    assert got.size == want.size and np.array_equal(got, want)

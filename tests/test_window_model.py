@@ -1,0 +1,35 @@
+"""CPU: tools/emulate_window.c, the plain-C model of the window-parallel compressor
+(csrc/compress_window.cuh: 32 positions per round; csrc/compress_wide.cuh: WW windows per round with
+table re-validation), must reproduce the oracle's bytes on the reference's fixtures.  This pins the
+ALGORITHM of the kernels where no GPU is available; the kernels themselves are checked in
+test_gpu_parity.py."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import DATA, ROOT
+
+FILES = ["alice29.txt", "html", "urls.10K", "geo.protodata", "kppkn.gtb", "fireworks.jpeg", "random1.bin",
+         "smallrandom1.bin", "sample-tweet.json"]
+
+
+@pytest.fixture(scope="module")
+def model(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("model") / "emulate_window")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tools", "emulate_window.c"),
+                           os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    return exe
+
+
+@pytest.mark.parametrize("ww", [None, "2", "4"])
+def test_window_model_matches_oracle(model, ww):
+    env = dict(os.environ)
+    if ww:
+        env["WW"] = ww
+    out = subprocess.run([model] + [os.path.join(DATA, f) for f in FILES], env=env, capture_output=True,
+                         text=True, check=True).stdout
+    lines = [l for l in out.splitlines() if "fragments" in l]
+    assert len(lines) == len(FILES)
+    for l in lines:
+        assert " 0 mismatches" in l, l
