@@ -277,19 +277,29 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
             const bool ready = ((pending >> lane) & 1u) && elen <= kShortElem && need <= frontier;
             if (ready) {
                 u8* d = o + dst;
-                if (is_copy) {
+                if (is_copy && eoff < elen) {
                     const u8* s = o + (dst - eoff);
-                    if (eoff >= elen) {
-                        for (u32 i = 0; i < elen; i++) d[i] = s[i];
-                    } else {
-                        for (u32 i = 0, k = 0; i < elen; i++) {  // pattern of `offset` bytes repeats
-                            d[i] = s[k];
-                            k = (k + 1 == eoff) ? 0 : k + 1;
-                        }
+                    for (u32 i = 0, k = 0; i < elen; i++) {  // pattern of `offset` bytes repeats
+                        d[i] = s[k];
+                        k = (k + 1 == eoff) ? 0 : k + 1;
                     }
                 } else {
-                    const u8* s = src + lsrc;
-                    for (u32 i = 0; i < elen; i++) d[i] = __ldg(s + i);
+                    // <= 16 source bytes through the aligned words that hold them (only words with at least
+                    // one wanted byte are read), then one predicated byte store per position: no loop
+                    const uintptr_t sa = reinterpret_cast<uintptr_t>(is_copy ? o + (dst - eoff) : src + lsrc);
+                    const volatile u32* w = reinterpret_cast<const volatile u32*>(sa & ~(uintptr_t)3);
+                    const u32 sh = (u32)sa << 3;
+                    const u32 last = (((u32)sa & 3u) + elen - 1u) >> 2;  // index of the last word needed (0..4)
+                    const u32 w0 = w[0];
+                    const u32 w1 = last >= 1 ? w[1] : 0u, w2 = last >= 2 ? w[2] : 0u, w3 = last >= 3 ? w[3] : 0u,
+                              w4 = last >= 4 ? w[4] : 0u;
+                    const u32 b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh),
+                              b2 = __funnelshift_r(w2, w3, sh), b3 = __funnelshift_r(w3, w4, sh);
+#pragma unroll
+                    for (u32 i = 0; i < 16; i++) {
+                        const u32 word = i < 4 ? b0 : (i < 8 ? b1 : (i < 12 ? b2 : b3));
+                        if (i < elen) d[i] = (u8)(word >> (8 * (i & 3)));
+                    }
                 }
             }
             __syncwarp();
