@@ -287,12 +287,23 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
                     // <= 16 source bytes through the aligned words that hold them (only words with at least
                     // one wanted byte are read), then one predicated byte store per position: no loop
                     const uintptr_t sa = reinterpret_cast<uintptr_t>(is_copy ? o + (dst - eoff) : src + lsrc);
-                    const volatile u32* w = reinterpret_cast<const volatile u32*>(sa & ~(uintptr_t)3);
+                    const u32* w = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
                     const u32 sh = (u32)sa << 3;
                     const u32 last = (((u32)sa & 3u) + elen - 1u) >> 2;  // index of the last word needed (0..4)
-                    const u32 w0 = w[0];
-                    const u32 w1 = last >= 1 ? w[1] : 0u, w2 = last >= 2 ? w[2] : 0u, w3 = last >= 3 ? w[3] : 0u,
-                              w4 = last >= 4 ? w[4] : 0u;
+                    u32 w0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+                    if (is_copy) {  // output bytes written earlier in this kernel: coherent loads
+                        w0 = w[0];
+                        if (last >= 1) w1 = w[1];
+                        if (last >= 2) w2 = w[2];
+                        if (last >= 3) w3 = w[3];
+                        if (last >= 4) w4 = w[4];
+                    } else {  // input: read-only path
+                        w0 = __ldg(w);
+                        if (last >= 1) w1 = __ldg(w + 1);
+                        if (last >= 2) w2 = __ldg(w + 2);
+                        if (last >= 3) w3 = __ldg(w + 3);
+                        if (last >= 4) w4 = __ldg(w + 4);
+                    }
                     const u32 b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh),
                               b2 = __funnelshift_r(w2, w3, sh), b3 = __funnelshift_r(w3, w4, sh);
 #pragma unroll

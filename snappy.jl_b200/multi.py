@@ -16,9 +16,35 @@ assembly into one all_to_all_single with split sizes taken from the gathered siz
 The codec calls are injected (`codec`), so the same host logic runs under gloo on CPU tensors in
 the tests (with the oracle as the stand-in codec) and under NCCL with the CUDA path in production.
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+_TRACE = bool(os.environ.get("SNAPPY_B200_TRACE_MULTI"))
+
+
+class _Trace:
+    """SNAPPY_B200_TRACE_MULTI=1: rank 0 prints where the time of a call went (synchronising marks)."""
+
+    def __init__(self, name):
+        self.name, self.marks = name, []
+        if _TRACE:
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def mark(self, what):
+        if _TRACE:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.marks.append("%s %.2f" % (what, (now - self.t) * 1e3))
+            self.t = now
+
+    def done(self):
+        if _TRACE and dist.get_rank() == 0:
+            print("[multi] %s: %s ms" % (self.name, " | ".join(self.marks)), flush=True)
 
 FRAGMENT = 65536
 
@@ -81,10 +107,12 @@ def compress_streams(shards, total_lens, codec, group=None):
     rank = dist.get_rank(group)
     assert len(shards) == world == len(total_lens)
     dev = shards[0].device
+    tr = _Trace("compress_streams")
     if hasattr(codec, "compress_shards"):
         pairs = codec.compress_shards(shards, total_lens)
     else:
         pairs = [codec.compress_shard(shards[s], total_lens[s]) for s in range(world)]
+    tr.mark("codec")
     segs = [p[0] for p in pairs]
     frag_sizes = [p[1].to(torch.int64) for p in pairs]
     # exchange 1: compressed byte counts (the path's only data-dependent global fact)
@@ -92,6 +120,7 @@ def compress_streams(shards, total_lens, codec, group=None):
     matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(matrix, mine, group=group)
     matrix = matrix.view(world, world).cpu()          # matrix[r][s] = bytes rank r made for stream s
+    tr.mark("sizes")
     in_splits = [int(x) for x in matrix[rank]]
     out_splits = [int(matrix[r][rank]) for r in range(world)]
     hdr = encode_header(total_lens[rank])
@@ -99,7 +128,9 @@ def compress_streams(shards, total_lens, codec, group=None):
     stream[: len(hdr)] = torch.frombuffer(bytearray(hdr), dtype=torch.uint8).to(dev)
     # exchange 2: segment assembly -- every segment lands at header + exclusive-scan offset
     send = torch.cat(segs) if world > 1 else segs[0]
+    tr.mark("alloc+cat")
     dist.all_to_all_single(stream[len(hdr):], send, out_splits, in_splits, group=group)
+    tr.mark("all_to_all")
     # side index of my stream: fragment sizes of every rank's run, in rank order
     nf_mine = torch.tensor([int(x.numel()) for x in frag_sizes], dtype=torch.int64, device=dev)
     nf_matrix = torch.empty(world * world, dtype=torch.int64, device=dev)
@@ -112,6 +143,8 @@ def compress_streams(shards, total_lens, codec, group=None):
     index = torch.empty(all_sizes.numel() + 1, dtype=torch.int64, device=dev)
     index[0] = len(hdr)
     index[1:] = len(hdr) + torch.cumsum(all_sizes, 0)
+    tr.mark("index")
+    tr.done()
     return stream, index
 
 
