@@ -42,6 +42,7 @@ __device__ __forceinline__ u32 ldg32u(const u8* p) {
 // probe offsets of the skip heuristic (skip starts at 32, step = skip >> 5, :162-172); filled once
 // by k_init_probe_offsets.  Only scan rounds past the first 32 probes read it (incompressible data).
 __device__ u32 g_probe_offsets[kChainPoEntries];
+__device__ u32 g_dbg_skip_emit = 0;  // upper-bound experiments: what would free emission buy
 
 __global__ void k_init_probe_offsets() {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -128,6 +129,10 @@ struct Chain {
         }
         const u32 pos = op + incl - sz;
         op += __shfl_sync(kFullMask, incl, 31);
+        if (g_dbg_skip_emit) {  // measurement only (option dbg_skip_emit): sizes stay right, bytes are not written
+            nrec = 0;
+            return;
+        }
         if (ll) {
             const u32 nm1 = ll - 1;
             if (ll < 60) {

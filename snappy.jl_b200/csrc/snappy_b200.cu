@@ -69,6 +69,7 @@ struct Options {
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
     int pipe_chunk_frags = (int)kPipeChunkFragsDefault;  // host-buffer API pipeline granularity
     int parse_chunk_log2 = (int)kParseChunkLog2;  // index-free parse: log2 of the compressed bytes per thread
+    int uncompress_segments = 8;  // streamed host-buffer uncompress: segments the stream is parsed in (2, 4 or 8)
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
 };
@@ -128,6 +129,11 @@ void apply_option(const char* name, int value) {
     }
     else if (!strcmp(name, "parse_chunk_log2")) g_ctx.opt.parse_chunk_log2 = value < 9 ? 9 : (value > 16 ? 16 : value);
     else if (!strcmp(name, "l2_persist")) g_ctx.opt.l2_persist = value;
+    else if (!strcmp(name, "uncompress_segments")) g_ctx.opt.uncompress_segments = value;
+    else if (!strcmp(name, "dbg_skip_emit")) {
+        const u32 v = (u32)value;
+        cudaMemcpyToSymbol(g_dbg_skip_emit, &v, 4);
+    }
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
     else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
@@ -962,7 +968,8 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
 // segment is still on its way up.  Returns -1 when the stream needs the whole-stream paths (not
 // fragment-clean, anomalies): the caller then runs them on the resident copy.
 int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32 claimed, u8* out) {
-    const int kChunks = 16, kSegs = 4;
+    const int kChunks = 16;
+    const int kSegs = (c.opt.uncompress_segments == 2 || c.opt.uncompress_segments == 8) ? c.opt.uncompress_segments : 4;
     const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
     cudaStream_t st = c.s_comp;
     u8* d_in = (u8*)c.stage_in.p;
