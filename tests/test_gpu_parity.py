@@ -323,3 +323,50 @@ def test_compress_kernel_variants_bit_exact(dev, oracle, options):
         for k, v in defaults.items():
             dev.set_option(k, v)
     assert got.size == want.size and np.array_equal(got, want)
+
+
+def test_streamed_uncompress_foreign_and_corrupt(snappy, oracle):
+    """> 64 MiB through the host-buffer C ABI takes the streamed uncompress (the stream is parsed in
+    segments while it uploads).  A foreign encoder's stream must decode, and a stream corrupted inside a
+    late segment must end with the oracle's status (the whole-stream paths arbitrate)."""
+    from snappy_jl_b200 import synth
+    raw = synth.mix(1400, seed=123, tail=31337)          # ~92 MB, compresses to ~41 MB ... make it bigger
+    raw = np.concatenate([raw, synth.source_like(96 << 20, seed=9)])   # > 64 MiB of compressed bytes
+    ours = oracle.compress_np(raw)
+    assert ours.size > (64 << 20)
+    assert np.array_equal(snappy.uncompress_np(ours), raw)
+    pa = pytest.importorskip("pyarrow")
+    theirs = np.frombuffer(pa.Codec("snappy").compress(raw.tobytes()).to_pybytes(), dtype=np.uint8)
+    if theirs.size > (64 << 20):
+        assert np.array_equal(snappy.uncompress_np(theirs), raw)
+    # corrupt one tag deep inside the stream (segment 6 of 8): same verdict as the reference
+    bad = ours.copy()
+    pos = int(bad.size * 0.7)
+    bad[pos: pos + 3] = (0xFF, 0xFF, 0xFF)               # 4-byte-offset copy tag with a huge offset
+    want = oracle.status_of_uncompress(bad.tobytes())
+    if want == oracle.OK:
+        assert np.array_equal(snappy.uncompress_np(bad), oracle.uncompress_np(bad))
+    else:
+        with pytest.raises(snappy.SnappyError) as e:
+            snappy.uncompress_np(bad)
+        assert e.value.status == want
+
+
+@pytest.mark.parametrize("shift", [1, 3, 8, 13])
+def test_unaligned_device_pointers(dev, oracle, shift):
+    """device buffers that start at odd addresses (the ring staging and the far-candidate loads of
+    the window kernel take their byte-wise forms) and odd-length tails"""
+    import torch
+    from snappy_jl_b200 import synth
+    raw = synth.mix(24, seed=31, tail=12345)
+    base = torch.zeros(raw.size + 64, dtype=torch.uint8, device="cuda")
+    view = base[shift: shift + raw.size]
+    view.copy_(to_dev(raw))
+    want = oracle.compress_np(raw)
+    stream, index = dev.compress_device(view, want_index=True)
+    assert np.array_equal(stream.cpu().numpy(), want)
+    out = torch.zeros(raw.size + 64, dtype=torch.uint8, device="cuda")
+    sview = torch.zeros(want.size + 64, dtype=torch.uint8, device="cuda")[shift: shift + want.size]
+    sview.copy_(stream)
+    back = dev.uncompress_device(sview, out=out[shift: shift + raw.size], index=index, claimed=raw.size)
+    assert np.array_equal(back.cpu().numpy(), raw)
