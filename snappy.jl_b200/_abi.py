@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnappy_b200.so")
+# SNAPPY_B200_LIB: another build of the same library (A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("SNAPPY_B200_LIB") or os.path.join(_HERE, "libsnappy_b200.so")
 
 OK = 0
 INPUT_TOO_LARGE = 1

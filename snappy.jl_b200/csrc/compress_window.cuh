@@ -35,6 +35,10 @@ namespace sb200 {
 
 constexpr u32 kRingChunk = 512;  // bytes staged per step (one 16-byte load per lane)
 constexpr u32 kRingAhead = 64;   // bytes past the window start that must be resident
+#ifndef SB200_FAR_ALL
+#define SB200_FAR_ALL 1
+#endif
+constexpr bool kFarAll = SB200_FAR_ALL != 0;
 
 template <bool kSmemTable>
 struct Win : Chain<kSmemTable> {
@@ -157,6 +161,9 @@ struct Win : Chain<kSmemTable> {
                 const u32* g = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
                 const u32 tb = t & ~3u, tsh = (nearp ? t : (u32)ga) << 3;
                 u32 c0, c1, c2 = 0, c3 = 0, c4 = 0;
+                // far_all: old candidates fetch all 16 bytes at once (one L2 round trip, more wavefronts)
+                // instead of 4 bytes first and the other 12 on a hit
+                const u32 far_all = kFarAll ? 1u : 0u;
                 asm volatile(
                     "{\n"
                     ".reg .pred p;\n"
@@ -168,14 +175,18 @@ struct Win : Chain<kSmemTable> {
                     "@p ld.shared.u32 %4, [%10];\n"
                     "@!p ld.global.nc.u32 %0, [%11];\n"
                     "@!p ld.global.nc.u32 %1, [%11+4];\n"
+                    "setp.ne.and.u32 p, %12, 0, !p;\n"
+                    "@p ld.global.nc.u32 %2, [%11+8];\n"
+                    "@p ld.global.nc.u32 %3, [%11+12];\n"
+                    "@p ld.global.nc.u32 %4, [%11+16];\n"
                     "}\n"
                     : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
                     : "r"(nearp), "r"(Rs + (tb & rmask)), "r"(Rs + ((tb + 4u) & rmask)),
                       "r"(Rs + ((tb + 8u) & rmask)), "r"(Rs + ((tb + 12u) & rmask)),
-                      "r"(Rs + ((tb + 16u) & rmask)), "l"(g)
+                      "r"(Rs + ((tb + 16u) & rmask)), "l"(g), "r"(far_all)
                     : "memory");
                 u32 C0 = __funnelshift_r(c0, c1, tsh);
-                const bool more = V && !nearp && C0 == B0;
+                const bool more = V && !nearp && !far_all && C0 == B0;
                 if (__any_sync(kFullMask, more)) {
                     if (more) {
                         c2 = __ldg(g + 2);
