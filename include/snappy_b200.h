@@ -146,6 +146,25 @@ int snappy_b200_parse_header(const uint8_t *in, size_t n, uint32_t *value, size_
  * reference's tests call directly (test/runtests.jl:172).  0-based, `limit` exclusive. */
 size_t snappy_b200_find_match_length(const uint8_t *a, size_t i1, size_t i2, size_t limit);
 
+/* ---- side-index sidecar ----------------------------------------
+ * The side index (nfrag + 1 offsets of the 64 KiB fragments inside a stream) lets any consumer
+ * take the indexed decoder without the parse.  It cannot travel inside the stream (the format has
+ * no room: a reference decoder would read a trailer as elements), so it travels NEXT to it, as a
+ * small self-describing blob:
+ *   "SB2IDX1\0" | u32 nfrag | u32 reserved | u64 uncompressed_len | u64 stream_len |
+ *   varint(index[0]) varint(index[1]-index[0]) ... varint(index[nfrag]-index[nfrag-1]) | u32 fnv1a
+ * All host code, no GPU.  A sidecar that does not match its stream can never change a result:
+ * the indexed decoder validates every fragment and falls back to the index-free paths. */
+size_t snappy_b200_index_pack_bound(size_t nfrag);
+/* index: HOST array of nfrag + 1 offsets (index[0] = header length, index[nfrag] = stream length).
+ * *out_len: in = capacity, out = bytes written. */
+int snappy_b200_index_pack(const uint64_t *index, size_t nfrag, uint64_t uncompressed_len,
+                           uint8_t *out, size_t *out_len);
+/* *nfrag: in = capacity of index in fragments (index holds capacity + 1 entries), out = fragments.
+ * Returns SNAPPY_B200_INVALID_INPUT for a malformed / truncated / checksum-failing sidecar. */
+int snappy_b200_index_unpack(const uint8_t *in, size_t n, uint64_t *index, size_t *nfrag,
+                             uint64_t *uncompressed_len, uint64_t *stream_len);
+
 /* ---- instrumentation (bench.py roofline) ------------------------------------------------- */
 
 /* Device time, in milliseconds, of the dominant kernel of the last compress (which=0) or

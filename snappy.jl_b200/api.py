@@ -111,3 +111,31 @@ def find_match_length(a, i1, i2, limit):
     if not (0 <= i1 <= i2 <= limit <= arr.size):
         raise ValueError("find_match_length: need 0 <= i1 <= i2 <= limit <= len(a)")
     return _abi.lib().snappy_b200_find_match_length(_ptr(arr), i1, i2, limit)
+
+
+# ---- side-index sidecar (include/snappy_b200.h) --------------------------
+
+def pack_index(index, uncompressed_len):
+    """`index`: the nfrag + 1 fragment offsets of a stream (as returned by device.compress_device(...,
+    want_index=True), on the host).  Returns the sidecar bytes that travel next to the stream."""
+    idx = np.ascontiguousarray(np.asarray(index), dtype=np.uint64).reshape(-1)
+    nfrag = idx.size - 1
+    out = np.empty(_abi.lib().snappy_b200_index_pack_bound(nfrag), dtype=np.uint8)
+    n = ctypes.c_size_t(out.size)
+    _check(_abi.lib().snappy_b200_index_pack(_ptr(idx), nfrag, int(uncompressed_len), _ptr(out), ctypes.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def unpack_index(sidecar):
+    """Inverse of pack_index: (index as uint64 array of nfrag + 1 offsets, uncompressed_len, stream_len).
+    Raises SnappyError("Invalid input.") for a malformed sidecar."""
+    a = _as_u8(sidecar)
+    nfrag = ctypes.c_size_t(0)
+    ulen, slen = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _check(_abi.lib().snappy_b200_index_unpack(_ptr(a), a.size, None, ctypes.byref(nfrag), ctypes.byref(ulen),
+                                               ctypes.byref(slen)))
+    idx = np.empty(nfrag.value + 1, dtype=np.uint64)
+    cap = ctypes.c_size_t(nfrag.value)
+    _check(_abi.lib().snappy_b200_index_unpack(_ptr(a), a.size, _ptr(idx), ctypes.byref(cap), ctypes.byref(ulen),
+                                               ctypes.byref(slen)))
+    return idx, ulen.value, slen.value

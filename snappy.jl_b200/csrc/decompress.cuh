@@ -232,9 +232,11 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
         u32 jump = (size >= 32u - lane || size >= rem) ? 32u : lane + size;
         const bool leaves = jump == 32u;
         // ---- positions reachable from lane 0 (the chain enters every window at its first byte)
+        // (every element is at least 2 bytes long, so the chain has at most 16 positions in a window:
+        // 4 rounds of doubling reach hops 0..15)
         u32 R = 1u;
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
+        for (int r = 0; r < 4; r++) {
             const u32 m = (((R >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u;
             R |= __reduce_or_sync(kFullMask, m);
             const u32 j2 = __shfl_sync(kFullMask, jump, jump & 31u);

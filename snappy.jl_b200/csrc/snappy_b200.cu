@@ -1336,6 +1336,84 @@ float snappy_b200_last_kernel_ms(int which) {
     return (which == 0 || which == 1) ? g_ctx.last_ms[which] : 0.f;
 }
 
+// ---- side-index sidecar (host only) ---------------------------------------------------------
+static const char kIdxMagic[8] = {'S', 'B', '2', 'I', 'D', 'X', '1', 0};
+
+static u32 fnv1a(const u8* p, size_t n) {
+    u32 h = 2166136261u;
+    for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 16777619u;
+    return h;
+}
+
+size_t snappy_b200_index_pack_bound(size_t nfrag) { return 8 + 4 + 4 + 8 + 8 + (nfrag + 1) * 10 + 4; }
+
+int snappy_b200_index_pack(const uint64_t* index, size_t nfrag, uint64_t uncompressed_len, uint8_t* out,
+                           size_t* out_len) {
+    if (!index || !out || !out_len || nfrag > 0xffffffffull) return SNAPPY_B200_BAD_ARGUMENT;
+    if (*out_len < snappy_b200_index_pack_bound(nfrag)) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    u8* p = out;
+    memcpy(p, kIdxMagic, 8);
+    p += 8;
+    const u32 nf = (u32)nfrag, zero = 0;
+    memcpy(p, &nf, 4);
+    memcpy(p + 4, &zero, 4);
+    memcpy(p + 8, &uncompressed_len, 8);
+    memcpy(p + 16, &index[nfrag], 8);
+    p += 24;
+    u64 prev = 0;
+    for (size_t i = 0; i <= nfrag; i++) {
+        if (index[i] < prev) return SNAPPY_B200_BAD_ARGUMENT;  // offsets never decrease
+        u64 d = index[i] - prev;
+        prev = index[i];
+        while (d >= 0x80) {
+            *p++ = (u8)(d | 0x80);
+            d >>= 7;
+        }
+        *p++ = (u8)d;
+    }
+    const u32 h = fnv1a(out, (size_t)(p - out));
+    memcpy(p, &h, 4);
+    p += 4;
+    *out_len = (size_t)(p - out);
+    return SNAPPY_B200_OK;
+}
+
+int snappy_b200_index_unpack(const uint8_t* in, size_t n, uint64_t* index, size_t* nfrag,
+                             uint64_t* uncompressed_len, uint64_t* stream_len) {
+    if (!in || !nfrag) return SNAPPY_B200_BAD_ARGUMENT;
+    if (n < 8 + 24 + 1 + 4 || memcmp(in, kIdxMagic, 8) != 0) return SNAPPY_B200_INVALID_INPUT;
+    u32 nf, h;
+    u64 ulen, slen;
+    memcpy(&nf, in + 8, 4);
+    memcpy(&ulen, in + 16, 8);
+    memcpy(&slen, in + 24, 8);
+    memcpy(&h, in + n - 4, 4);
+    if (fnv1a(in, n - 4) != h) return SNAPPY_B200_INVALID_INPUT;
+    if ((u64)nf != (ulen + kBlockSize - 1) / kBlockSize) return SNAPPY_B200_INVALID_INPUT;
+    if (index && *nfrag < nf) return SNAPPY_B200_BUFFER_TOO_SMALL;
+    const u8* p = in + 32;
+    const u8* end = in + n - 4;
+    u64 cur = 0;
+    for (u64 i = 0; i <= nf; i++) {
+        u64 d = 0;
+        int shift = 0;
+        for (;;) {
+            if (p >= end || shift > 63) return SNAPPY_B200_INVALID_INPUT;
+            const u8 b = *p++;
+            d |= (u64)(b & 0x7f) << shift;
+            shift += 7;
+            if (!(b & 0x80)) break;
+        }
+        cur += d;
+        if (index) index[i] = cur;
+    }
+    if (p != end || cur != slen) return SNAPPY_B200_INVALID_INPUT;
+    *nfrag = nf;
+    if (uncompressed_len) *uncompressed_len = ulen;
+    if (stream_len) *stream_len = slen;
+    return SNAPPY_B200_OK;
+}
+
 int snappy_b200_last_launch_count(int which) {
     std::unique_lock<std::mutex> lk(g_ctx.mu);
     return (which == 0 || which == 1) ? g_ctx.last_launches[which] : 0;

@@ -91,6 +91,37 @@ function find_match_length(a::Vector{UInt8}, i1::Integer, i2::Integer, limit::In
     end
 end
 
+# Side-index sidecar (include/snappy_b200.h): `index` holds the nfrag + 1 fragment offsets a
+# device-resident compress returned; the sidecar travels next to the stream and lets a consumer take
+# the indexed decoder (snappy_b200_uncompress_device with d_frag_index) without the parse.
+function pack_index(index::Vector{UInt64}, uncompressed_len::Integer)
+    nfrag = length(index) - 1
+    out = Vector{UInt8}(undef, ccall((:snappy_b200_index_pack_bound, LIB), Csize_t, (Csize_t,), nfrag))
+    outlen = Ref{Csize_t}(length(out))
+    GC.@preserve index out begin
+        _check(ccall((:snappy_b200_index_pack, LIB), Cint,
+                     (Ptr{UInt64}, Csize_t, UInt64, Ptr{UInt8}, Ref{Csize_t}),
+                     index, nfrag, uncompressed_len, out, outlen))
+    end
+    resize!(out, outlen[])
+end
+
+function unpack_index(sidecar::Vector{UInt8})
+    nfrag = Ref{Csize_t}(0)
+    ulen = Ref{UInt64}(0)
+    slen = Ref{UInt64}(0)
+    GC.@preserve sidecar begin
+        _check(ccall((:snappy_b200_index_unpack, LIB), Cint,
+                     (Ptr{UInt8}, Csize_t, Ptr{UInt64}, Ref{Csize_t}, Ref{UInt64}, Ref{UInt64}),
+                     sidecar, length(sidecar), C_NULL, nfrag, ulen, slen))
+        index = Vector{UInt64}(undef, nfrag[] + 1)
+        _check(ccall((:snappy_b200_index_unpack, LIB), Cint,
+                     (Ptr{UInt8}, Csize_t, Ptr{UInt64}, Ref{Csize_t}, Ref{UInt64}, Ref{UInt64}),
+                     sidecar, length(sidecar), index, nfrag, ulen, slen))
+        return index, ulen[], slen[]
+    end
+end
+
 # Optional: pick the device / create the context up front (otherwise lazy on first call).
 init(device::Integer = -1) = _check(ccall((:snappy_b200_init, LIB), Cint, (Cint,), device))
 

@@ -98,3 +98,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "snappy_oracle" not in text and "liboracle" not in text, f
+
+
+def test_index_sidecar_roundtrip_and_rejects(snappy):
+    """side-index sidecar: host-only pack / unpack"""
+    rng = np.random.default_rng(5)
+    for nfrag, total in ((1, 1), (1, 65536), (3, 3 * 65536 - 17), (1000, 1000 * 65536)):
+        sizes = rng.integers(1, 76490, size=nfrag)
+        index = np.concatenate([[5], 5 + np.cumsum(sizes)]).astype(np.uint64)
+        side = snappy.pack_index(index, total)
+        back, ulen, slen = snappy.unpack_index(side)
+        assert np.array_equal(back, index) and ulen == total and slen == int(index[-1])
+        assert len(side) < 40 + 3 * (nfrag + 1)          # ~2-3 bytes per fragment
+        for cut in (0, 7, len(side) - 1):
+            with pytest.raises(snappy.SnappyError):
+                snappy.unpack_index(side[:cut])
+        bad = bytearray(side)
+        bad[len(bad) // 2] ^= 0x40
+        with pytest.raises(snappy.SnappyError):
+            snappy.unpack_index(bytes(bad))
+    with pytest.raises(snappy.SnappyError):                 # nfrag does not match the length
+        snappy.unpack_index(snappy.pack_index(np.array([1, 9, 20], dtype=np.uint64), 65536))
+    with pytest.raises(snappy.SnappyError):                 # decreasing offsets
+        snappy.pack_index(np.array([5, 4], dtype=np.uint64), 10)

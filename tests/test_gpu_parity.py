@@ -370,3 +370,24 @@ def test_unaligned_device_pointers(dev, oracle, shift):
     sview.copy_(stream)
     back = dev.uncompress_device(sview, out=out[shift: shift + raw.size], index=index, claimed=raw.size)
     assert np.array_equal(back.cpu().numpy(), raw)
+
+
+def test_index_sidecar_drives_the_indexed_decoder(dev, snappy, oracle):
+    """compress on the device, ship stream + sidecar, decode with the unpacked index; a sidecar of
+    ANOTHER stream must not change the result (every fragment is validated)"""
+    import torch
+    from snappy_jl_b200 import synth
+    raw = synth.mix(40, seed=8, tail=999)
+    other = synth.mix(40, seed=9, tail=999)
+    stream, index = dev.compress_device(to_dev(raw), want_index=True)
+    _, index2 = dev.compress_device(to_dev(other), want_index=True)
+    side = snappy.pack_index(index.cpu().numpy().astype(np.uint64), raw.size)
+    assert len(side) < 200
+    idx, ulen, slen = snappy.unpack_index(side)
+    assert ulen == raw.size and slen == stream.numel()
+    back = dev.uncompress_device(stream, index=torch.from_numpy(idx.astype(np.int64)).cuda(), claimed=ulen)
+    assert np.array_equal(back.cpu().numpy(), raw)
+    assert dev.last_launch_count(1) <= 2                       # indexed decoder only, no parse
+    wrong, _, _ = snappy.unpack_index(snappy.pack_index(index2.cpu().numpy().astype(np.uint64), other.size))
+    back = dev.uncompress_device(stream, index=torch.from_numpy(wrong.astype(np.int64)).cuda(), claimed=ulen)
+    assert np.array_equal(back.cpu().numpy(), raw)
