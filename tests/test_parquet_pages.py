@@ -1,0 +1,72 @@
+"""Parquet-page adapter (BASELINE config 4's real-world caller): every SNAPPY page
+body of a Parquet file written by pyarrow decodes on the GPU, in one batched call, to what pyarrow's own
+(foreign) snappy decoder and the oracle produce; the writer side compresses pages to the oracle's bytes."""
+import io
+
+import numpy as np
+import pytest
+
+pa = pytest.importorskip("pyarrow")
+pq = pytest.importorskip("pyarrow.parquet")
+
+
+def make_file(version, page_size, rows=120_000):
+    rng = np.random.default_rng(11)
+    words = np.array(["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta"])
+    t = pa.table({
+        "id": np.arange(rows, dtype=np.int64),
+        "bucket": rng.integers(0, 50, rows).astype(np.int32),
+        "price": np.round(rng.normal(100, 15, rows), 2),
+        "tag": words[rng.integers(0, len(words), rows)],
+        "text": ["row %d of the %s partition" % (i, words[i % 8]) for i in range(rows)],
+    })
+    buf = io.BytesIO()
+    pq.write_table(t, buf, compression="snappy", data_page_size=page_size, data_page_version=version,
+                   use_dictionary=["bucket", "tag"], row_group_size=rows // 2)
+    return buf.getvalue()
+
+
+def test_thrift_page_headers_cover_every_column_chunk():
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("1.0", 4096, rows=20_000)
+    pages = pp.list_pages(f)
+    md = pq.ParquetFile(io.BytesIO(f)).metadata
+    total = sum(md.row_group(r).column(c).total_compressed_size for r in range(md.num_row_groups)
+                for c in range(md.num_columns))
+    # headers + bodies tile the column chunks exactly
+    assert sum(p["compressed"] + p["prefix"] for p in pages) < total
+    assert len(pages) > 50 and all(p["codec"] in ("SNAPPY", "UNCOMPRESSED") for p in pages)
+    assert any(p["kind"] == pp.DICTIONARY_PAGE for p in pages)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version,page_size", [("1.0", 4096), ("2.0", 4096), ("1.0", 1 << 20)])
+def test_parquet_pages_decode_on_gpu(oracle, version, page_size):
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file(version, page_size)
+    pages, out, offs = pp.uncompress_pages(f)
+    codec = pa.Codec("snappy")
+    n_snappy = 0
+    for p, o in zip(pages, offs):
+        if p["codec"] != "SNAPPY" or p["compressed"] == 0:
+            continue
+        n_snappy += 1
+        body = f[p["stream"]: p["stream"] + p["compressed"]]
+        want = codec.decompress(body, decompressed_size=p["uncompressed"]).to_pybytes()
+        got = out[o: o + p["uncompressed"]].tobytes()
+        assert got == want
+        if n_snappy % 37 == 0:
+            assert oracle.uncompress(body) == want
+    assert n_snappy > (200 if page_size == 4096 else 8)
+
+
+@pytest.mark.gpu
+def test_parquet_pages_compress_on_gpu(oracle):
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("1.0", 4096, rows=30_000)
+    pages, out, offs = pp.uncompress_pages(f)
+    raw_pages = [out[o: o + p["uncompressed"]].tobytes() for p, o in zip(pages, offs) if o >= 0]
+    ours = pp.compress_pages(raw_pages)
+    assert len(ours) == len(raw_pages)
+    for a, b in zip(ours, raw_pages):
+        assert a == oracle.compress(b)
