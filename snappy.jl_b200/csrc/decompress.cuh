@@ -162,7 +162,7 @@ k_decode_serial(const u8* __restrict__ in, u64 L, u64 ip0, u8* __restrict__ out,
 // below the `frontier` (the destination of the first unfinished element of the batch).
 // Anything that is not a clean, self-contained fragment sets res->fallback and the caller reruns
 // the exact serial decoder, so a wrong index can never change the result.
-constexpr u32 kDecodeWarpsPerCta = 4;
+constexpr u32 kDecodeWarpsPerCta = 2;   // small CTAs: finished warps free their slot sooner (5.60 -> 5.53 ms)
 
 // Decode the self-contained element run in[ip .. ie) into o[0 .. on).  Returns false when the run
 // is not clean (bad element, reaches before o, does not end exactly at ie / on).
@@ -337,7 +337,7 @@ struct DecodeDesc {
 };
 
 template <int kMinBlocks>
-__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, kMinBlocks)
+__global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, kMinBlocks * 4 / kDecodeWarpsPerCta)
 k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag, u32 first,
                    u32 count, u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
                    DecodeResult* __restrict__ res, const DecodeDesc* __restrict__ descs = nullptr,

@@ -14,4 +14,4 @@ ncu --set full --clock-control none --import-source on -k regex:k_compress_windo
     -o gpurun_out/prof_window_l2_$tag python tools/prof_run.py 16384 0 smem_chains=0 > gpurun_out/ncu_b_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_decode_fragments -s 1 -c 1 -f \
     -o gpurun_out/prof_decode_$tag python tools/prof_run.py 16384 0 > gpurun_out/ncu_c_$tag.log 2>&1
-tail -2 gpurun_out/ncu_a_$tag.log gpurun_out/ncu_b_$tag.log gpurun_out/ncu_c_$tag.log
+for f in a b c; do tail -n 2 gpurun_out/ncu_${f}_$tag.log; done
