@@ -71,4 +71,41 @@ __device__ __forceinline__ u32 lds32u(const u8* base, u32 q) {
     return __funnelshift_r(w[0], w[1], (q & 3u) * 8u);
 }
 
+// dst[0 .. len) = src[0 .. len), non-overlapping (or src at least 16 bytes below dst): 16-byte aligned
+// stores; the source is read as the aligned words that hold each 16-byte group and funnel-shifted, so
+// the two misalignments need not agree.  kReadOnly: src is input (read-only path), else output bytes
+// this kernel wrote earlier (coherent loads).
+template <bool kReadOnly>
+__device__ __forceinline__ void warp_copy_forward(u8* __restrict__ dst, const u8* src, u64 len, u32 lane) {
+    if (len < 64) {
+        for (u64 i = lane; i < len; i += 32) dst[i] = src[i];
+        return;
+    }
+    const u64 head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    for (u64 i = lane; i < head; i += 32) dst[i] = src[i];
+    const u64 nvec = (len - head) >> 4;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
+    const u32* sw = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+    const u32 sh = (u32)sa << 3;
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (u64 j = lane; j < nvec; j += 32) {
+        const u32* p = sw + 4 * j;
+        u32 w0, w1, w2, w3, w4;
+        if (kReadOnly) {
+            w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3);
+            w4 = (sh & 31u) ? __ldg(p + 4) : 0u;  // the fifth word only when the source is misaligned
+        } else {
+            w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3];
+            w4 = (sh & 31u) ? p[4] : 0u;
+        }
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh);
+        v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh);
+        v.w = __funnelshift_r(w3, w4, sh);
+        d4[j] = v;
+    }
+    for (u64 i = head + (nvec << 4) + lane; i < len; i += 32) dst[i] = src[i];
+}
+
 }  // namespace sb200

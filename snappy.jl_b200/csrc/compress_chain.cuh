@@ -233,7 +233,8 @@ struct Chain {
                     if (lh > 3) out[op + 3] = (u8)(nm1 >> 16);
                 }
             }
-            for (u32 k = lane; k < ll; k += 32) out[op + lh + k] = __ldg(F + lit_from + k);
+            __syncwarp();
+            warp_copy_forward<true>(out + op + lh, F + lit_from, ll, lane);  // 16-byte stores when long
             op += lh + ll;
         }
     }
