@@ -93,8 +93,8 @@ k_compress_wide(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift
     const u32 c = wi / kW, k = wi % kW;
     const u32 bar_id = 1u + c, bar_n = 32u * kW;
     u16* T = reinterpret_cast<u16*>(smem) + (size_t)c * kMaxTableEntries;
-    const u32 ring = smem_u32(smem) + chains * kMaxTableEntries * 2u + c * ring_bytes;
-    WideCtl<kW>* ctl = reinterpret_cast<WideCtl<kW>*>(smem + (size_t)chains * (kMaxTableEntries * 2u + ring_bytes)) + c;
+    const u32 ring = smem_u32(smem) + chains * kMaxTableEntries * 2u + c * (ring_bytes + kRingMirror);
+    WideCtl<kW>* ctl = reinterpret_cast<WideCtl<kW>*>(smem + (size_t)chains * (kMaxTableEntries * 2u + ring_bytes + kRingMirror)) + c;
     volatile WideCtl<kW>* vc = ctl;
     if (k == 0 && lane == 0) {
         for (int j = 0; j < 4; j++) mbar_init(&ctl->tok[j], 1);

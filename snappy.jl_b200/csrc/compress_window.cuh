@@ -35,6 +35,7 @@ namespace sb200 {
 
 constexpr u32 kRingChunk = 512;  // bytes staged per step (one 16-byte load per lane)
 constexpr u32 kRingAhead = 64;   // bytes past the window start that must be resident
+constexpr u32 kRingMirror = 32;  // the first bytes of the ring are repeated behind its end: a 20-byte read never wraps
 #ifndef SB200_FAR_ALL
 #define SB200_FAR_ALL 1
 #endif
@@ -56,10 +57,16 @@ struct Win : Chain<kSmemTable> {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
         return v;
     }
-    // unaligned 32-bit load at position p (lo <= p, p + 8 <= hi)
+    template <int kOff>
+    static __device__ __forceinline__ u32 lds32o(u32 a) {  // word at a + kOff (immediate offset: no address math)
+        u32 v;
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(kOff) : "memory");
+        return v;
+    }
+    // unaligned 32-bit load at position p (lo <= p, p + 8 <= hi); reads may run into the mirror
     __device__ __forceinline__ u32 ring32u(u32 p) const {
-        const u32 q = p & ~3u;
-        return __funnelshift_r(lds32(Rs + (q & rmask)), lds32(Rs + ((q + 4u) & rmask)), p << 3);
+        const u32 a = Rs + ((p & ~3u) & rmask);
+        return __funnelshift_r(lds32o<0>(a), lds32o<4>(a), p << 3);
     }
     // stage chunks until [.., upto) is resident or the fragment is exhausted
     __device__ __forceinline__ void stage_to(u32 upto) {
@@ -79,9 +86,14 @@ struct Win : Chain<kSmemTable> {
                 v.z = ldg32u(F + p + 8);
                 v.w = ldg32u(F + p + 12);
             }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + (p & rmask)), "r"(v.x), "r"(v.y),
+            const u32 ro = p & rmask;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + ro), "r"(v.x), "r"(v.y),
                          "r"(v.z), "r"(v.w)
                          : "memory");
+            if (ro < kRingMirror)  // mirror of the ring's first bytes behind its end
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + rmask + 1u + ro), "r"(v.x),
+                             "r"(v.y), "r"(v.z), "r"(v.w)
+                             : "memory");
             hi += kRingChunk;
         }
         lo = hi > rmask + 1u ? hi - (rmask + 1u) : 0u;
@@ -143,9 +155,9 @@ struct Win : Chain<kSmemTable> {
                 u32 B0, B1, B2, B3;
                 {
                     const u32 qb = q & ~3u, sh = q << 3;
-                    const u32 w0 = lds32(Rs + (qb & rmask)), w1 = lds32(Rs + ((qb + 4u) & rmask)),
-                              w2 = lds32(Rs + ((qb + 8u) & rmask)), w3 = lds32(Rs + ((qb + 12u) & rmask)),
-                              w4 = lds32(Rs + ((qb + 16u) & rmask));
+                    const u32 ab = Rs + (qb & rmask);
+                    const u32 w0 = lds32o<0>(ab), w1 = lds32o<4>(ab), w2 = lds32o<8>(ab), w3 = lds32o<12>(ab),
+                              w4 = lds32o<16>(ab);
                     B0 = __funnelshift_r(w0, w1, sh);
                     B1 = __funnelshift_r(w1, w2, sh);
                     B2 = __funnelshift_r(w2, w3, sh);
@@ -169,21 +181,19 @@ struct Win : Chain<kSmemTable> {
                     ".reg .pred p;\n"
                     "setp.ne.u32 p, %5, 0;\n"
                     "@p ld.shared.u32 %0, [%6];\n"
-                    "@p ld.shared.u32 %1, [%7];\n"
-                    "@p ld.shared.u32 %2, [%8];\n"
-                    "@p ld.shared.u32 %3, [%9];\n"
-                    "@p ld.shared.u32 %4, [%10];\n"
-                    "@!p ld.global.nc.u32 %0, [%11];\n"
-                    "@!p ld.global.nc.u32 %1, [%11+4];\n"
-                    "setp.ne.and.u32 p, %12, 0, !p;\n"
-                    "@p ld.global.nc.u32 %2, [%11+8];\n"
-                    "@p ld.global.nc.u32 %3, [%11+12];\n"
-                    "@p ld.global.nc.u32 %4, [%11+16];\n"
+                    "@p ld.shared.u32 %1, [%6+4];\n"
+                    "@p ld.shared.u32 %2, [%6+8];\n"
+                    "@p ld.shared.u32 %3, [%6+12];\n"
+                    "@p ld.shared.u32 %4, [%6+16];\n"
+                    "@!p ld.global.nc.u32 %0, [%7];\n"
+                    "@!p ld.global.nc.u32 %1, [%7+4];\n"
+                    "setp.ne.and.u32 p, %8, 0, !p;\n"
+                    "@p ld.global.nc.u32 %2, [%7+8];\n"
+                    "@p ld.global.nc.u32 %3, [%7+12];\n"
+                    "@p ld.global.nc.u32 %4, [%7+16];\n"
                     "}\n"
                     : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
-                    : "r"(nearp), "r"(Rs + (tb & rmask)), "r"(Rs + ((tb + 4u) & rmask)),
-                      "r"(Rs + ((tb + 8u) & rmask)), "r"(Rs + ((tb + 12u) & rmask)),
-                      "r"(Rs + ((tb + 16u) & rmask)), "l"(g), "r"(far_all)
+                    : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
                     : "memory");
                 u32 C0 = __funnelshift_r(c0, c1, tsh);
                 const bool more = V && !nearp && !far_all && C0 == B0;
@@ -342,7 +352,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
     const u32 gwarp = blockIdx.x * nwarp + warp;
     u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * kMaxTableEntries
                         : gtables + (size_t)gwarp * kMaxTableEntries;
-    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * kMaxTableEntries * 2u : 0u) + warp * ring_bytes;
+    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * kMaxTableEntries * 2u : 0u) + warp * (ring_bytes + kRingMirror);
     const u32 lane = lane_id();
     for (;;) {
         if (reserve && *reinterpret_cast<volatile u32*>(counter) + reserve >= nfrag) break;

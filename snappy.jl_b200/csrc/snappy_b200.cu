@@ -331,10 +331,10 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         u32 ctas = (nfrag + chains - 1) / chains;
         if (ctas > (u32)c.sm_count) ctas = (u32)c.sm_count;
         if (c.opt.wide == 4)
-            k_compress_wide<4><<<ctas, chains * 128, (size_t)chains * (kMaxTableEntries * 2 + ra + sizeof(WideCtl<4>)), st>>>(
+            k_compress_wide<4><<<ctas, chains * 128, (size_t)chains * (kMaxTableEntries * 2 + ra + kRingMirror + sizeof(WideCtl<4>)), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, descs, ndesc, ra);
         else
-            k_compress_wide<2><<<ctas, chains * 64, (size_t)chains * (kMaxTableEntries * 2 + ra + sizeof(WideCtl<2>)), st>>>(
+            k_compress_wide<2><<<ctas, chains * 64, (size_t)chains * (kMaxTableEntries * 2 + ra + kRingMirror + sizeof(WideCtl<2>)), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, descs, ndesc, ra);
         *launches += 1;
         return SNAPPY_B200_OK;
@@ -343,7 +343,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
     if (ctas_a) {
         if (window)
-            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra), st>>>(
+            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
                 ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
         else
@@ -369,7 +369,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             CU(cudaStreamSetAttribute(c.side, cudaStreamAttributeAccessPolicyWindow, &av));
         }
         if (window)
-            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * rb, c.side>>>(
+            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
                 gate ? gate->div : 1u);
