@@ -63,7 +63,7 @@ struct Options {
     int ring_l2 = 1024;         // history ring per global-table warp
     int spec_smem = 32;         // copy end positions pre-probed per step by shared-table warps (1..32)
     int spec_l2 = 16;           // same for global-table warps (each probing lane costs an L1tex wavefront)
-    int l2_chains = 12;         // warps per CTA of the global-table (L2) kernel, <= 14
+    int l2_chains = 10;         // warps per CTA of the global-table (L2) kernel, <= 14
     int l2_ctas = 1;            // CTAs per SM of that kernel (1..3): l2_ctas x l2_chains extra chains per SM
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12

@@ -309,7 +309,7 @@ def test_compress_kernel_variants_bit_exact(dev, oracle, options):
     kernel with both table placements running side by side)"""
     import torch
     from snappy_jl_b200 import synth
-    defaults = {"window": 1, "wide": 0, "l2_chains": 12, "smem_chains": 6}
+    defaults = {"window": 1, "wide": 0, "l2_chains": 10, "smem_chains": 6}
     raw = np.concatenate([synth.mix(96, seed=5, tail=777),
                           np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
                                         dtype=np.uint8)])

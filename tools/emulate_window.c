@@ -47,6 +47,9 @@ static void init_po(void) { uint32_t skip = 32, off = 0; PO[0] = 0; for (int i =
 
 enum { ARR = 0, SCAN = 1 };
 
+/* bytes compared per lane (the kernels use 16; CAP=32 models "16 more for lanes that match all 16", which saved
+ * rounds but cost more instructions than it saved on the GPU: 28.2 vs 27.0 ms); CAP equal bytes go to the whole-warp extension */
+static uint32_t CAP = 16;
 static size_t compress_fragment_window(Frag *f) {
     const uint8_t *F = f->F; const long n = f->n, lim = n - 16; f->lim = lim; f->op = f->out;
     memset(f->T, 0, sizeof f->T);
@@ -80,7 +83,7 @@ static size_t compress_fragment_window(Frag *f) {
                 H[l] = V[l] ? hashw(f, ld32(F + q)) : (0x80000000u | (uint32_t)l);
                 t[l] = V[l] ? f->T[H[l]] : 0; dup[l] = 0;
                 for (int j = 0; j < l; j++) if (H[j] == H[l]) dup[l] = 1;
-                uint32_t k = 0; if (V[l]) while (k < 16 && F[t[l] + k] == F[q + k]) k++;
+                uint32_t k = 0; if (V[l]) while (k < CAP && q + k < n && F[t[l] + k] == F[q + k]) k++;
                 m[l] = k;
             }
             uint32_t ins = 0; int fin = 0, next_mode = -1; long next_a = 0;
@@ -93,7 +96,7 @@ static size_t compress_fragment_window(Frag *f) {
                     if (l > 0) ins |= 1u << (l - 1);
                     ins |= 1u << l;
                     if (m[l] >= 4) {
-                        if (m[l] == 16) { slow_ip = a + l; slow_cand = t[l]; break; }
+                        if (m[l] == CAP) { slow_ip = a + l; slow_cand = t[l]; break; }
                         record(f, lit_from, a + l, t[l], m[l]); lit_from = a + l + m[l];
                         long tgt = l + m[l];
                         if (a + tgt >= lim) { fin = 1; break; }
@@ -116,7 +119,7 @@ static size_t compress_fragment_window(Frag *f) {
                 if (a + e - scan_s >= 32) { next_mode = SCAN; next_a = a + e; break; }
                 if (dup[e] && e > 0) { next_mode = SCAN; next_a = a + e; break; }
                 ins |= 1u << e; /* hit */
-                if (m[e] == 16) { slow_ip = a + e; slow_cand = t[e]; break; }
+                if (m[e] == CAP) { slow_ip = a + e; slow_cand = t[e]; break; }
                 record(f, lit_from, a + e, t[e], m[e]); lit_from = a + e + m[e];
                 long tgt = e + m[e];
                 if (a + tgt >= lim) { fin = 1; break; }
@@ -127,7 +130,7 @@ static size_t compress_fragment_window(Frag *f) {
             for (int k = 0; k < 32; k++) if (ins >> k & 1) f->T[hashw(f, ld32(F + a + k))] = (uint16_t)(a + k);
             if (slow_ip >= 0) { /* long copy: full-length compare */
                 f->slow++;
-                long M = 16; while (slow_ip + M < n && F[slow_cand + M] == F[slow_ip + M]) M++;
+                long M = CAP; while (slow_ip + M < n && F[slow_cand + M] == F[slow_ip + M]) M++;
                 record(f, lit_from, slow_ip, slow_cand, M); lit_from = slow_ip + M;
                 if (lit_from >= lim) break;
                 mode = ARR; a = lit_from; continue;
@@ -253,6 +256,7 @@ static size_t compress_fragment_multi(Frag *f) {
 int main(int argc, char **argv) {
     init_po();
     if (getenv("WW")) WW = atoi(getenv("WW"));
+    if (getenv("CAP")) CAP = (uint32_t)atoi(getenv("CAP"));
     for (int ai = 1; ai < argc; ai++) {
         FILE *fp = fopen(argv[ai], "rb"); if (!fp) { perror(argv[ai]); return 1; }
         fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);

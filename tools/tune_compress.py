@@ -16,10 +16,10 @@ for kv in sys.argv[3:]:  # global library options, e.g. window=1
 for cfg in (sys.argv[2] if len(sys.argv) > 2 else '6,0,2;6,14,2').split(';'):
     v = [int(x) for x in cfg.split(',')]
     sm, l2, rs = v[:3]
-    ss, sl = (v[3], v[4]) if len(v) >= 5 else (32, 32)
+    ss, sl = (v[3], v[4]) if len(v) >= 5 else (32, 16)
     nc = v[5] if len(v) >= 6 else 1
     device.set_option("l2_ctas", nc)
-    rs_, rl_ = (v[6], v[7]) if len(v) >= 8 else (4096, 2048)
+    rs_, rl_ = (v[6], v[7]) if len(v) >= 8 else (2048, 1024)  # the library defaults
     device.set_option("ring_smem", rs_)
     device.set_option("ring_l2", rl_)
     device.set_option("l2_reserve", rs)
