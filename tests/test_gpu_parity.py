@@ -391,3 +391,75 @@ def test_index_sidecar_drives_the_indexed_decoder(dev, snappy, oracle):
     wrong, _, _ = snappy.unpack_index(snappy.pack_index(index2.cpu().numpy().astype(np.uint64), other.size))
     back = dev.uncompress_device(stream, index=torch.from_numpy(wrong.astype(np.int64)).cuda(), claimed=ulen)
     assert np.array_equal(back.cpu().numpy(), raw)
+
+
+def _adversarial(rng, n):
+    """byte patterns aimed at the window kernel: repeats at distances around the 32-lane window, the ring
+    size and its staging chunk, equal 4-grams inside one window, runs, near-copies with single-byte edits"""
+    kind = int(rng.integers(0, 7))
+    if kind == 0:      # short period
+        p = rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)
+        return np.resize(p, n)
+    if kind == 1:      # period near the ring / chunk sizes
+        per = int(rng.choice([511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097]))
+        p = rng.integers(0, 256, per, dtype=np.uint8)
+        return np.resize(p, n)
+    if kind == 2:      # words from a tiny alphabet: many equal 4-grams inside 32 bytes
+        words = [bytes(rng.integers(97, 100, int(rng.integers(1, 6)), dtype=np.uint8)) for _ in range(6)]
+        out = bytearray()
+        while len(out) < n:
+            out += words[int(rng.integers(0, len(words)))]
+        return np.frombuffer(bytes(out[:n]), dtype=np.uint8)
+    if kind == 3:      # runs of random length
+        out = np.empty(n, dtype=np.uint8)
+        i = 0
+        while i < n:
+            l = int(rng.integers(1, 200))
+            out[i:i + l] = rng.integers(0, 256)
+            i += l
+        return out
+    if kind == 4:      # a block repeated with single-byte edits (copies of 16..31 bytes, long copies)
+        blk = rng.integers(0, 256, int(rng.integers(40, 3000)), dtype=np.uint8)
+        out = np.resize(blk, n).copy()
+        idx = rng.integers(0, max(n, 1), max(n // int(rng.integers(17, 300)), 1))
+        out[idx] ^= 0x55
+        return out
+    if kind == 5:      # random with planted repeats at window-ish distances
+        out = rng.integers(0, 256, n, dtype=np.uint8)
+        for _ in range(n // 64):
+            d = int(rng.choice([4, 5, 8, 16, 31, 32, 33, 63, 64, 65, 96, 127, 128]))
+            l = int(rng.integers(4, 40))
+            s = int(rng.integers(0, max(n - d - l, 1)))
+            out[s + d: s + d + l] = out[s: s + l][: max(0, min(l, n - s - d))]
+        return out
+    return rng.integers(0, 4, n, dtype=np.uint8)   # 2-bit noise: dense hash collisions
+
+
+def test_adversarial_patterns_bit_exact(dev, oracle):
+    """differential test against the oracle on inputs built to stress the window kernel's trust rules,
+    its ring and the decoder's window parse; both table placements"""
+    rng = np.random.default_rng(20261018)
+    for it in range(120):
+        n = int(rng.choice([0, 1, 14, 15, 16, 17, 100, 4095, 4096, 65535, 65536, 65537, 70000, 131072 + 13,
+                            int(rng.integers(1, 300000))]))
+        raw = _adversarial(rng, n) if n else np.empty(0, dtype=np.uint8)
+        want = oracle.compress_np(raw)
+        opts = [{"l2_chains": 0}, {"smem_chains": 0}][it % 2]
+        try:
+            for k, v in opts.items():
+                dev.set_option(k, v)
+            stream, index = dev.compress_device(to_dev(raw) if n else torch_empty(), want_index=True)
+        finally:
+            dev.set_option("l2_chains", 10)
+            dev.set_option("smem_chains", 6)
+        got = stream.cpu().numpy()
+        assert got.size == want.size and np.array_equal(got, want), "compress differs (case %d, n=%d)" % (it, n)
+        back = dev.uncompress_device(stream, index=index, claimed=n)
+        assert np.array_equal(back.cpu().numpy(), raw)
+        back = dev.uncompress_device(stream, claimed=n)     # index-free parse
+        assert np.array_equal(back.cpu().numpy(), raw)
+
+
+def torch_empty():
+    import torch
+    return torch.empty(0, dtype=torch.uint8, device="cuda")
