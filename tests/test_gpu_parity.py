@@ -463,3 +463,24 @@ def test_adversarial_patterns_bit_exact(dev, oracle):
 def torch_empty():
     import torch
     return torch.empty(0, dtype=torch.uint8, device="cuda")
+
+
+@pytest.mark.parametrize("nfrag,tail", [(2049, 0), (3072, 1), (4096, 0)])
+def test_streamed_host_paths_boundaries(snappy, oracle, nfrag, tail):
+    """host-buffer API right above the streaming thresholds: chunk-aligned and ragged sizes"""
+    from snappy_jl_b200 import synth
+    raw = synth.mix(nfrag, seed=400 + nfrag, tail=tail)
+    got = snappy.compress_np(raw)
+    want = oracle.compress_np(raw)
+    assert got.size == want.size and np.array_equal(got, want)
+    assert np.array_equal(snappy.uncompress_np(want), raw)
+
+
+def test_streamed_uncompress_incompressible(snappy, oracle):
+    """a > 64 MiB stream made of 64 KiB literals only: every segment boundary falls inside a literal"""
+    from snappy_jl_b200 import synth
+    raw = synth.random_bytes(80 << 20, seed=77)
+    want = oracle.compress_np(raw)
+    assert want.size > raw.size
+    assert np.array_equal(snappy.uncompress_np(want), raw)
+    assert np.array_equal(snappy.compress_np(raw), want)
