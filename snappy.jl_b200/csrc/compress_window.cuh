@@ -40,6 +40,9 @@ constexpr u32 kRingMirror = 32;  // the first bytes of the ring are repeated beh
 #define SB200_FAR_ALL 1
 #endif
 constexpr bool kFarAll = SB200_FAR_ALL != 0;
+#ifndef SB200_M_BRANCHFREE
+#define SB200_M_BRANCHFREE 1
+#endif
 
 template <bool kSmemTable>
 struct Win : Chain<kSmemTable> {
@@ -208,11 +211,19 @@ struct Win : Chain<kSmemTable> {
                 {
                     const u32 x0 = C0 ^ B0, x1 = __funnelshift_r(c1, c2, tsh) ^ B1,
                               x2 = __funnelshift_r(c2, c3, tsh) ^ B2, x3 = __funnelshift_r(c3, c4, tsh) ^ B3;
+#if SB200_M_BRANCHFREE
+                    // equal bytes per word (0..4), then the length of the run of full words: no divergent branches
+                    const u32 m0 = x0 ? ((u32)__ffs((int)x0) - 1u) >> 3 : 4u, m1 = x1 ? ((u32)__ffs((int)x1) - 1u) >> 3 : 4u,
+                              m2 = x2 ? ((u32)__ffs((int)x2) - 1u) >> 3 : 4u, m3 = x3 ? ((u32)__ffs((int)x3) - 1u) >> 3 : 4u;
+                    const bool f0 = m0 == 4u, f1 = f0 && m1 == 4u, f2 = f1 && m2 == 4u;
+                    m = m0 + (f0 ? m1 : 0u) + (f1 ? m2 : 0u) + (f2 ? m3 : 0u);
+#else
                     if (x0) m = ((u32)__ffs((int)x0) - 1u) >> 3;
                     else if (x1) m = 4u + (((u32)__ffs((int)x1) - 1u) >> 3);
                     else if (x2) m = 8u + (((u32)__ffs((int)x2) - 1u) >> 3);
                     else if (x3) m = 12u + (((u32)__ffs((int)x3) - 1u) >> 3);
                     else m = 16u;
+#endif
                     if (!V) m = 0;
                 }
                 const u32 vmask = __ballot_sync(kFullMask, V);
@@ -229,30 +240,21 @@ struct Win : Chain<kSmemTable> {
                     const u32 rest = (lane < 31u) ? (stop_all >> (lane + 1u)) : 0u;
                     const u32 es = lane + (u32)__ffs((int)rest);  // first event lane of a scan from lane + 1
                     const u32 ebit = 1u << (es & 31u);
-                    u32 kind, e;
-                    ins = lbit | (lbit >> 1);  // :233,:235
-                    if (hitmask & lbit) {
-                        kind = K_COPY;
-                        e = lane;
-                    } else if (!rest) {
-                        kind = K_LEAVE;
-                        e = 0;
-                        if (lane < 31u) ins |= ~0u << (lane + 1u);
-                    } else {
-                        e = es;
-                        ins |= (ebit - 1u) & (~0u << (lane + 1u));
-                        if (!(vmask & ebit)) kind = K_FIN;  // :175
-                        else if (dupmask & ebit) kind = K_NEXTSCAN;
-                        else {
-                            kind = K_COPY;
-                            ins |= ebit;  // :191
-                        }
-                    }
-                    if (lane && (dupmask & lbit)) {  // untrusted lane: the next round starts here
-                        kind = K_NEXTARR;
-                        e = lane;
-                        ins = 0;
-                    }
+                    // (selects, no branches: the lanes differ in all of these)
+                    const bool hit = (hitmask & lbit) != 0u, none = rest == 0u;
+                    const bool ev_invalid = (vmask & ebit) == 0u, ev_dup = (dupmask & ebit) != 0u;  // :175
+                    const bool untrusted = lane != 0u && (dupmask & lbit) != 0u;  // the next round starts here
+                    const u32 above = (lane < 31u) ? (~0u << (lane + 1u)) : 0u;
+                    const u32 kind_scan = none ? (u32)K_LEAVE
+                                               : (ev_invalid ? (u32)K_FIN : (ev_dup ? (u32)K_NEXTSCAN : (u32)K_COPY));
+                    // a scan inserts every position up to its first event, and the event itself if it is a hit (:191)
+                    const u32 ins_scan = none ? above : (((ebit - 1u) & above) | ((ev_invalid || ev_dup) ? 0u : ebit));
+                    u32 kind = hit ? (u32)K_COPY : kind_scan;
+                    u32 e = hit ? lane : (none ? 0u : es);
+                    ins = lbit | (lbit >> 1) | (hit ? 0u : ins_scan);  // :233,:235
+                    kind = untrusted ? (u32)K_NEXTARR : kind;
+                    e = untrusted ? lane : e;
+                    ins = untrusted ? 0u : ins;
                     const u32 r = __shfl_sync(kFullMask, tm, e);  // candidate and length of the copy at e
                     if (kind == K_COPY && ((r >> 8) & 31u) == 16u) kind = K_SLOW;
                     desc = kind | (e << 3) | ((hitmask & lbit) ? 0u : (1u << 13)) | (r & 0xffff1f00u);
