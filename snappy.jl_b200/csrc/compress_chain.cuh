@@ -144,7 +144,22 @@ struct Chain {
                 if (lh > 3) out[pos + 3] = (u8)(nm1 >> 16);
             }
             if (ll <= 16) {
-                for (u32 k = 0; k < ll; k++) out[pos + lh + k] = __ldg(F + lf + k);
+                // <= 16 literal bytes through the aligned words that hold them (only words with a wanted byte are
+                // read), then one predicated byte store per position: no per-lane loop
+                const uintptr_t sa = reinterpret_cast<uintptr_t>(F + lf);
+                const u32* w = reinterpret_cast<const u32*>(sa & ~(uintptr_t)3);
+                const u32 sh = (u32)sa << 3;
+                const u32 last = (((u32)sa & 3u) + ll - 1u) >> 2;  // index of the last word needed (0..4)
+                const u32 w0 = __ldg(w), w1 = last >= 1 ? __ldg(w + 1) : 0u, w2 = last >= 2 ? __ldg(w + 2) : 0u,
+                          w3 = last >= 3 ? __ldg(w + 3) : 0u, w4 = last >= 4 ? __ldg(w + 4) : 0u;
+                const u32 b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh),
+                          b2 = __funnelshift_r(w2, w3, sh), b3 = __funnelshift_r(w3, w4, sh);
+                u8* d = out + pos + lh;
+#pragma unroll
+                for (u32 i = 0; i < 16; i++) {
+                    const u32 word = i < 4 ? b0 : (i < 8 ? b1 : (i < 12 ? b2 : b3));
+                    if (i < ll) d[i] = (u8)(word >> (8 * (i & 3)));
+                }
             }
         }
         u32 lm = __ballot_sync(kFullMask, ll > 16);  // long literals: whole warp, one after the other
