@@ -104,12 +104,20 @@ struct Win : Chain<kSmemTable> {
         __syncwarp();
     }
 
-    // whole-warp match extension from `M` known equal bytes (find_match_length, :344-387)
+    // whole-warp match extension from `M` known equal bytes (find_match_length, :344-387): 32 bytes per
+    // ballot, from the ring while both sides are resident there (dictionary-like data: the candidate is
+    // recent and the match ends within a few bytes), else from L1/L2
     __device__ __forceinline__ u32 extend(u32 ip, u32 cand, u32 M) const {
-        const u8* pa = F + cand + lane;
-        const u8* pb = F + ip + lane;
         while (ip + M < n) {
-            const u32 nq = __ballot_sync(kFullMask, __ldg(pa + M) != __ldg(pb + M));
+            u32 x, y;
+            if (cand + M >= lo && ip + M + 32u <= hi) {
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(x) : "r"(Rs + ((cand + M + lane) & rmask)) : "memory");
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(y) : "r"(Rs + ((ip + M + lane) & rmask)) : "memory");
+            } else {
+                x = __ldg(F + cand + M + lane);
+                y = __ldg(F + ip + M + lane);
+            }
+            const u32 nq = __ballot_sync(kFullMask, x != y);
             if (nq) {
                 M += (u32)__ffs((int)nq) - 1u;
                 break;
