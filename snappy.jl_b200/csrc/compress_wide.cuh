@@ -138,6 +138,7 @@ k_compress_wide(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift
         ch.Rs = ring;
         ch.rmask = ring_bytes - 1u;
         ch.lo = ch.hi = 0;
+        ch.pre_at = 0xffffffffu;
         ch.nstage = (n + kRingChunk - 1u) & ~(kRingChunk - 1u);
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
         ch.Qs = smem_u32(&ctl->rec[0]);

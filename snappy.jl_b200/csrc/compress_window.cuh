@@ -54,6 +54,8 @@ struct Win : Chain<kSmemTable> {
     // ring: positions [lo, hi) of the fragment at Rs + (position & rmask); hi is a multiple of 512
     u32 Rs, rmask, lo, hi, nstage;
     bool aligned16;
+    uint4 pre;   // chunk [pre_at, pre_at + 512) loaded ahead of time (one 16-byte group per lane)
+    u32 pre_at;
 
     static __device__ __forceinline__ u32 lds32(u32 a) {
         u32 v;
@@ -71,24 +73,32 @@ struct Win : Chain<kSmemTable> {
         const u32 a = Rs + ((p & ~3u) & rmask);
         return __funnelshift_r(lds32o<0>(a), lds32o<4>(a), p << 3);
     }
-    // stage chunks until [.., upto) is resident or the fragment is exhausted
+    // one chunk (16 bytes per lane) of the fragment at position p
+    __device__ __forceinline__ uint4 load_chunk(u32 p) const {
+        uint4 v;
+        if (aligned16) {
+            v = __ldg(reinterpret_cast<const uint4*>(F + p));
+        } else {
+            v.x = ldg32u(F + p);
+            v.y = ldg32u(F + p + 4);
+            v.z = ldg32u(F + p + 8);
+            v.w = ldg32u(F + p + 12);
+        }
+        return v;
+    }
+    // stage chunks until [.., upto) is resident or the fragment is exhausted.  The chunk behind the last
+    // one staged is already on its way (pre, loaded when the previous one was stored), so that the load
+    // latency is not exposed every 512 bytes.
     __device__ __forceinline__ void stage_to(u32 upto) {
         u32 from = lo;
         if (upto > hi + rmask + 1u) {  // a long copy ran past the ring: everything older is dropped
             hi = (upto - (rmask + 1u)) & ~(kRingChunk - 1u);
             from = hi;
+            pre_at = 0xffffffffu;
         }
         while (hi < upto && hi < nstage) {
             const u32 p = hi + lane * 16u;
-            uint4 v;
-            if (aligned16) {
-                v = __ldg(reinterpret_cast<const uint4*>(F + p));
-            } else {
-                v.x = ldg32u(F + p);
-                v.y = ldg32u(F + p + 4);
-                v.z = ldg32u(F + p + 8);
-                v.w = ldg32u(F + p + 12);
-            }
+            const uint4 v = (pre_at == hi) ? pre : load_chunk(p);
             const u32 ro = p & rmask;
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + ro), "r"(v.x), "r"(v.y),
                          "r"(v.z), "r"(v.w)
@@ -98,6 +108,10 @@ struct Win : Chain<kSmemTable> {
                              "r"(v.y), "r"(v.z), "r"(v.w)
                              : "memory");
             hi += kRingChunk;
+            if (hi < nstage) {  // the next chunk: issued now, stored when the window gets there
+                pre = load_chunk(hi + lane * 16u);
+                pre_at = hi;
+            }
         }
         lo = hi > rmask + 1u ? hi - (rmask + 1u) : 0u;
         if (lo < from) lo = from;
@@ -410,6 +424,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         ch.Rs = ring;
         ch.rmask = ring_bytes - 1u;
         ch.lo = ch.hi = 0;
+        ch.pre_at = 0xffffffffu;
         ch.nstage = (n + kRingChunk - 1u) & ~(kRingChunk - 1u);
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
         ch.run_window();
