@@ -73,11 +73,15 @@ struct Chain {
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(Ts + 2u * h) : "memory");
             return v;
         }
-        return __ldcg(T + h);
+        // global tables: keep their lines in L2 ahead of everything that streams through it (evict_last):
+        // -4 % kernel time, they are the randomly re-read state
+        u16 v;
+        asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; ld.global.cg.L2::cache_hint.u16 %0, [%1], pol; }" : "=h"(v) : "l"(T + h) : "memory");
+        return v;
     }
     __device__ __forceinline__ void tput(u32 h, u32 pos) const {
         if (kSmemTable) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
-        else __stcg(T + h, (u16)pos);
+        else asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; st.global.cg.L2::cache_hint.u16 [%0], %1, pol; }" ::"l"(T + h), "h"((u16)pos) : "memory");
     }
 
     // ---- emission ---------------------------------------------------------------------------
