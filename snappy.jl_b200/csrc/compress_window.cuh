@@ -364,7 +364,7 @@ struct Win : Chain<kSmemTable> {
 // Persistent warps, as k_compress_chain; each warp additionally owns `ring_bytes` of shared memory
 // (behind the tables for the shared-table variant).
 template <bool kSmemTable>
-__global__ void __launch_bounds__(kSmemTable ? 224 : 448, kSmemTable ? 1 : 2)
+__global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
 k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                   const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
                   u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,

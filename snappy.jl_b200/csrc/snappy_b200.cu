@@ -63,7 +63,7 @@ struct Options {
     int ring_l2 = 1024;         // history ring per global-table warp
     int spec_smem = 32;         // copy end positions pre-probed per step by shared-table warps (1..32)
     int spec_l2 = 16;           // same for global-table warps (each probing lane costs an L1tex wavefront)
-    int l2_chains = 10;         // warps per CTA of the global-table (L2) kernel, <= 14
+    int l2_chains = 14;         // warps per CTA of the global-table (L2) kernel, <= 20 (window kernel; <= 14 for the chain kernel)
     int l2_ctas = 1;            // CTAs per SM of that kernel (1..3): l2_ctas x l2_chains extra chains per SM
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
@@ -120,7 +120,7 @@ void apply_option(const char* name, int value) {
     if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
     else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
-    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
     else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
     else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
     else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
@@ -320,7 +320,9 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     u32* counter = (u32*)((u8*)c.result.p + 64);
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
-    const u32 wa = (u32)c.opt.smem_chains, wb = (u32)c.opt.l2_chains;
+    const u32 wa = (u32)c.opt.smem_chains;
+    // (the step-wise chain kernel is compiled for <= 14 warps per CTA)
+    const u32 wb = (!c.opt.window && c.opt.l2_chains > 14) ? 14u : (u32)c.opt.l2_chains;
     u32 ctas_a = wa ? (nfrag + wa - 1) / wa : 0u;  // smem_chains == 0: global-table warps only (profiling)
     if (ctas_a > (u32)c.sm_count) ctas_a = (u32)c.sm_count;
     const u32 warps_a = ctas_a * wa;
