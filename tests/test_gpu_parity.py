@@ -309,7 +309,7 @@ def test_compress_kernel_variants_bit_exact(dev, oracle, options):
     kernel with both table placements running side by side)"""
     import torch
     from snappy_jl_b200 import synth
-    defaults = {"window": 1, "wide": 0, "l2_chains": 10, "smem_chains": 6}
+    defaults = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6}
     raw = np.concatenate([synth.mix(96, seed=5, tail=777),
                           np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
                                         dtype=np.uint8)])
@@ -450,7 +450,7 @@ def test_adversarial_patterns_bit_exact(dev, oracle):
                 dev.set_option(k, v)
             stream, index = dev.compress_device(to_dev(raw) if n else torch_empty(), want_index=True)
         finally:
-            dev.set_option("l2_chains", 10)
+            dev.set_option("l2_chains", 14)
             dev.set_option("smem_chains", 6)
         got = stream.cpu().numpy()
         assert got.size == want.size and np.array_equal(got, want), "compress differs (case %d, n=%d)" % (it, n)

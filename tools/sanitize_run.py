@@ -17,7 +17,7 @@ for opts in ({}, {"l2_chains": 0}, {"smem_chains": 0}, {"window": 0}):
     stream, index = device.compress_device(d, want_index=True)
     back = device.uncompress_device(stream, index=index, claimed=raw.size)
     assert torch.equal(back, d)
-    for k, v in {"l2_chains": 10, "smem_chains": 6, "window": 1}.items():
+    for k, v in {"l2_chains": 14, "smem_chains": 6, "window": 1}.items():
         device.set_option(k, v)
 back = device.uncompress_device(stream, claimed=raw.size)       # index-free parse
 assert torch.equal(back, d)
