@@ -178,10 +178,12 @@ int ctx_init_locked(int device) {
     }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
-    // L2 persistence for the global hash tables of the global-table compress warps (see launch_chain_kernels)
+    // L2 set-aside for persisting / evict_last lines, at its maximum (79 MiB on B200): the global hash tables of
+    // the global-table compress warps are read and written with L2::evict_last hints and live there (13.2 ms with
+    // the set-aside, 14.1 ms without; SNAPPY_B200_NO_PERSIST_LIMIT=1 leaves the device default)
     c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (c.l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max);
+    if (c.l2_persist_max && !getenv("SNAPPY_B200_NO_PERSIST_LIMIT")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max);
     if (getenv("SNAPPY_B200_DEBUG"))
         fprintf(stderr, "[snappy_b200] L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", prop.l2CacheSize >> 20,
                 c.l2_persist_max >> 20, c.l2_window_max >> 20);
