@@ -172,7 +172,13 @@ int snappy_b200_index_unpack(const uint8_t *in, size_t n, uint64_t *index, size_
  * the launching stream around that kernel; and the number of kernels that call launched. */
 float snappy_b200_last_kernel_ms(int which);
 int snappy_b200_last_launch_count(int which);
-/* Selects kernel variants for A/B testing (0 = default).  See DESIGN.md. */
+/* Selects kernel variants for A/B testing (0 = default).  See DESIGN.md.
+ * One option changes the BYTES the compressor emits:
+ *   "rules" = 0  Snappy.jl's rules (src/internal.jl:127-329): the reference, default;
+ *           = 1  libsnappy <= 1.1.7 (ip_limit n-15, 60-byte literal with the short tag, table per fragment);
+ *           = 2  Google snappy >= 1.1.9 (as 1, bucket = (hash >> 17) & mask, up to 32768 buckets): byte-identical
+ *                to the C++ library current consumers link (checked against pyarrow's bundled codec).
+ * Every setting produces a valid Snappy stream that any decoder (this one, Snappy.jl, libsnappy) accepts. */
 void snappy_b200_set_option(const char *name, int value);
 
 #ifdef __cplusplus

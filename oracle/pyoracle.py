@@ -65,6 +65,8 @@ def lib():
                                              u8p, ctypes.c_void_p]
         L.sjo_compress.restype = ctypes.c_int
         L.sjo_compress.argtypes = [u8p, ctypes.c_size_t, u8p, szp]
+        L.sjo_compress_rules.restype = ctypes.c_int
+        L.sjo_compress_rules.argtypes = [u8p, ctypes.c_size_t, u8p, szp, ctypes.c_int]
         L.sjo_uncompressed_length.restype = ctypes.c_int
         L.sjo_uncompressed_length.argtypes = [u8p, ctypes.c_size_t, szp]
         L.sjo_uncompress_ex.restype = ctypes.c_int
@@ -102,6 +104,17 @@ def compress_np(data):
 
 def compress(data):
     return compress_np(data).tobytes()
+
+
+def compress_rules(data, rules):
+    """Google snappy's rules instead of the reference's (1 = libsnappy <= 1.1.7, 2 = snappy >= 1.1.9)."""
+    a = _as_u8(data)
+    out = np.empty(maxlength_compressed(a.size), dtype=np.uint8)
+    n = ctypes.c_size_t(out.size)
+    rc = lib().sjo_compress_rules(_ptr(a), a.size, _ptr(out), ctypes.byref(n), int(rules))
+    if rc != OK:
+        raise OracleError(rc)
+    return out[: n.value].tobytes()
 
 
 def compress_fragments(data, total_len, first_frag, nfrag):

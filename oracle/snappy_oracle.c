@@ -238,6 +238,109 @@ int sjo_compress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len) {
     return SJO_OK;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * libsnappy rules (option `rules` of the product).
+ * NOT a restatement of the reference: this is Google snappy's compressor (snappy.cc: Compress,
+ * WorkingMemory::GetHashTable, CompressFragment, EmitLiteral, EmitCopy), which Snappy.jl ports with the
+ * deviations of appendix B.4.  Differences from sjo_compress above, all of them:
+ *   ip_limit = n - 15 (kInputMarginBytes; the reference's inclusive end makes it n - 16);
+ *   a literal of exactly 60 bytes keeps the one-byte tag (n = len - 1 < 60);
+ *   the table is sized from each fragment's length (GetHashTable(num_to_read));
+ *   rules = 1 (libsnappy <= 1.1.7): bucket = (bytes * 0x1e35a7bd) >> (32 - log2(table size)), <= 16384 buckets;
+ *   rules = 2 (Google snappy >= 1.1.9): bucket = ((bytes * 0x1e35a7bd) >> 17) & (table size - 1), <= 32768.
+ * PINNING: rules = 2 is byte-identical to pyarrow's bundled Google snappy on every fixture file and on
+ * fuzzed inputs (tests/test_libsnappy_rules.py); rules = 1 differs from it only in the bucket function and
+ * table cap (no libsnappy 1.1.7 binary exists in this image: that one line is unpinned).
+ * The table holds positions directly, 0 = empty = fragment start. */
+size_t sjo_compress_fragment_rules(const uint8_t *F, size_t n_, uint8_t *out, uint16_t *table,
+                                   uint32_t entries, int rules) {
+    const long n = (long)n_;
+    uint32_t shift = 32;
+    for (uint32_t e = entries; e > 1; e >>= 1) shift--;
+    const uint32_t mask = entries - 1;
+#define BUCKET(w) (rules == 2 ? ((((uint32_t)(w) * 0x1e35a7bdu) >> 17) & mask) \
+                              : (((uint32_t)(w) * 0x1e35a7bdu) >> shift))
+    uint8_t *op = out;
+    long ip = 0, next_emit = 0, candidate = 0;
+    if (n >= K_INPUT_MARGIN_BYTES) {
+        const long ip_limit = n - K_INPUT_MARGIN_BYTES;
+        for (;;) {
+            uint32_t skip = 32;
+            ip += 1;
+            uint32_t next_hash = BUCKET(load32u(F + ip));
+            long next_ip = ip;
+            for (;;) {
+                ip = next_ip;
+                uint32_t h = next_hash;
+                uint32_t between = skip >> 5;
+                skip += between;
+                next_ip = ip + between;
+                if (next_ip > ip_limit) goto emit_remainder;
+                next_hash = BUCKET(load32u(F + next_ip));
+                candidate = table[h];
+                table[h] = (uint16_t)ip;
+                if (load32u(F + candidate) == load32u(F + ip)) break;
+            }
+            {   /* EmitLiteral: n = len - 1 < 60 takes the short tag */
+                size_t len = (size_t)(ip - next_emit);
+                if (len == 60) {
+                    *op++ = (uint8_t)(59u << 2);
+                    memcpy(op, F + next_emit, 60);
+                    op += 60;
+                } else {
+                    op = emit_literal(op, F + next_emit, len);
+                }
+            }
+            for (;;) {
+                long matched = 4;
+                while (ip + matched < n && F[candidate + matched] == F[ip + matched]) matched++;
+                op = emit_copy(op, (uint32_t)(ip - candidate), (uint32_t)matched);
+                ip += matched;
+                next_emit = ip;
+                if (ip >= ip_limit) goto emit_remainder;
+                table[BUCKET(load32u(F + ip - 1))] = (uint16_t)(ip - 1);
+                uint32_t cur = load32u(F + ip);
+                uint32_t h = BUCKET(cur);
+                candidate = table[h];
+                table[h] = (uint16_t)ip;
+                if (cur != load32u(F + candidate)) break;
+            }
+        }
+    }
+emit_remainder:
+    if (next_emit < n) {
+        size_t len = (size_t)(n - next_emit);
+        if (len == 60) {
+            *op++ = (uint8_t)(59u << 2);
+            memcpy(op, F + next_emit, 60);
+            op += 60;
+        } else {
+            op = emit_literal(op, F + next_emit, len);
+        }
+    }
+#undef BUCKET
+    return (size_t)(op - out);
+}
+
+/* snappy.cc Compress(): varint, then fragments of 65536 bytes, each with its own table size */
+int sjo_compress_rules(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len, int rules) {
+    if (rules == 0) return sjo_compress(in, n, out, out_len);
+    if (n > 0xffffffffull) return SJO_INPUT_TOO_LARGE;
+    if (*out_len < sjo_maxlength_compressed(n)) return SJO_BUFFER_TOO_SMALL;
+    static _Thread_local uint16_t table[2 * K_MAX_HASH_TABLE_SIZE];
+    const uint32_t cap = rules == 2 ? 2 * K_MAX_HASH_TABLE_SIZE : K_MAX_HASH_TABLE_SIZE;
+    uint8_t *op = out + sjo_encode32(out, (uint32_t)n);
+    for (size_t s = 0; s < n; s += K_BLOCK_SIZE) {
+        size_t fn = (n - s < K_BLOCK_SIZE) ? (n - s) : K_BLOCK_SIZE;
+        uint32_t entries = 256;
+        while (entries < cap && entries < fn) entries <<= 1;
+        memset(table, 0, entries * sizeof(uint16_t));
+        op += sjo_compress_fragment_rules(in + s, fn, op, table, entries, rules);
+    }
+    *out_len = (size_t)(op - out);
+    return SJO_OK;
+}
+
 /* Snappy.jl:90-92 */
 int sjo_uncompressed_length(const uint8_t *in, size_t n, size_t *result) {
     uint32_t v;

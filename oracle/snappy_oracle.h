@@ -53,6 +53,11 @@ size_t sjo_compress_fragment(const uint8_t *frag, size_t n, uint8_t *out, uint16
 size_t sjo_compress_fragments(const uint8_t *in, uint64_t total_len, size_t first_frag,
                               size_t nfrag, uint8_t *out, uint32_t *frag_sizes);
 int sjo_compress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
+/* Google snappy's own rules (NOT the reference's; see the .c file): rules 0 = sjo_compress, 1 = libsnappy
+ * <= 1.1.7, 2 = Google snappy >= 1.1.9 (pinned against pyarrow's bundled codec) */
+size_t sjo_compress_fragment_rules(const uint8_t *frag, size_t n, uint8_t *out, uint16_t *table,
+                                   uint32_t entries, int rules);
+int sjo_compress_rules(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len, int rules);
 int sjo_uncompressed_length(const uint8_t *in, size_t n, size_t *result);
 int sjo_uncompress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
 /* same as sjo_uncompress, additionally reports the output position at which the error fired */

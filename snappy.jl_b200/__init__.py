@@ -8,7 +8,7 @@ No CPU fallback: importing the codec entry points loads libsnappy_b200.so, and e
 fails with SnappyError when no sm_100 GPU is usable.
 """
 from . import _abi
-from .api import (SnappyError, pack_index, unpack_index, compress, compress_np, encode32, find_match_length,
+from .api import (SnappyError, pack_index, unpack_index, set_rules, compress, compress_np, encode32, find_match_length,
                   length_uncompressed, maxlength_compressed, parse32, uncompress, uncompress_np)
 
 K_BLOCK_SIZE = 65536          # src/internal.jl:31

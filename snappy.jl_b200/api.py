@@ -115,6 +115,14 @@ def find_match_length(a, i1, i2, limit):
 
 # ---- side-index sidecar (include/snappy_b200.h) --------------------------
 
+def set_rules(rules):
+    """Which compressor's bytes `compress` reproduces: 0 = Snappy.jl (the reference, default), 1 = libsnappy
+    <= 1.1.7, 2 = Google snappy >= 1.1.9 (what pyarrow / current C++ consumers produce).  SURVEY.md 8(f)4."""
+    if rules not in (0, 1, 2):
+        raise ValueError("rules must be 0, 1 or 2")
+    _abi.lib().snappy_b200_set_option(b"rules", int(rules))
+
+
 def pack_index(index, uncompressed_len):
     """`index`: the nfrag + 1 fragment offsets of a stream (as returned by device.compress_device(...,
     want_index=True), on the host).  Returns the sidecar bytes that travel next to the stream."""

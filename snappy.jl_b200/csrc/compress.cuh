@@ -17,12 +17,13 @@ struct FragEmitter {
     u8* out;   // scratch slot of this fragment (global)
     u32 op;    // bytes written so far (warp-uniform)
     u32 lane;
+    u32 lit_short = 60;  // literals below this take the one-byte header: 60 = Snappy.jl (:271), 61 = libsnappy (option `rules`)
 
     // src/internal.jl:252-287 -- tag, then the bytes.  lanes copy the literal cooperatively.
     __device__ __forceinline__ void literal(const u8* F, u32 from, u32 len) {
         u32 n = len - 1;
         u32 hdr;
-        if (len < 60) {  // :271 (a 60-byte literal takes the 2-byte header, like the reference)
+        if (len < lit_short) {  // :271 (a 60-byte literal takes the 2-byte header, like the reference)
             hdr = 1;
             if (lane == 0) out[op] = (u8)(n << 2);
         } else {
@@ -145,10 +146,13 @@ __device__ __forceinline__ void reset_table(u16* T, u32 shift, u32 lane) {
 // Serial form of compress_fragment! (src/internal.jl:127-250), executed warp-uniformly: every
 // lane follows the same decisions; lanes cooperate on match extension and literal copies.
 // F: fragment in shared memory (n bytes + zero pad), T: zeroed table, shift = 32 - log2(entries).
+// kLib (option `rules`): libsnappy's ip_limit = n - 15 and bucket = ((w * mul) >> shift) & hmask.
+template <bool kLib = false>
 __device__ __forceinline__ void compress_fragment_serial(const u8* F, u16* T, const u32 n,
-                                                         const u32 shift, FragEmitter& em) {
+                                                         const u32 shift, FragEmitter& em, const u32 hmask = ~0u) {
     const u32 lane = em.lane;
-    const int lim = (int)n - 16;  // ip_limit, 0-based (src/internal.jl:131)
+    const int lim = (int)n - (kLib ? 15 : 16);  // ip_limit, 0-based (src/internal.jl:131)
+    auto bucket = [&](u32 w) { return kLib ? (((w * kHashMul) >> shift) & hmask) : ((w * kHashMul) >> shift); };
     u32 ip = 0, next_emit = 0;
 
     if (n >= kInputMargin) {
@@ -157,7 +161,7 @@ __device__ __forceinline__ void compress_fragment_serial(const u8* F, u16* T, co
             u32 skip = 32;
             ip += 1;
             u32 next_ip = ip;
-            u32 next_hash = (lds32u(F, ip) * kHashMul) >> shift;
+            u32 next_hash = bucket(lds32u(F, ip));
             u32 cand = 0;
             bool bail = false;
             for (;;) {
@@ -167,7 +171,7 @@ __device__ __forceinline__ void compress_fragment_serial(const u8* F, u16* T, co
                 skip += between;
                 next_ip = ip + between;
                 if ((int)next_ip > lim) { bail = true; break; }  // :175
-                next_hash = (lds32u(F, next_ip) * kHashMul) >> shift;
+                next_hash = bucket(lds32u(F, next_ip));
                 cand = T[h];
                 __syncwarp();
                 if (lane == 0) T[h] = (u16)ip;
@@ -184,8 +188,8 @@ __device__ __forceinline__ void compress_fragment_serial(const u8* F, u16* T, co
                 next_emit = ip;
                 if ((int)ip >= lim) { bail = true; break; }  // :222
                 u32 w = lds32u(F, ip);
-                u32 hp = (lds32u(F, ip - 1) * kHashMul) >> shift;
-                u32 hc = (w * kHashMul) >> shift;
+                u32 hp = bucket(lds32u(F, ip - 1));
+                u32 hc = bucket(w);
                 __syncwarp();
                 if (lane == 0) T[hp] = (u16)(ip - 1);  // :233
                 __syncwarp();
@@ -612,11 +616,13 @@ k_compress_fragments_serial(const u8* __restrict__ g_in, u64 shard_len, u32 shif
 // own varint header, table sized from the page length).  Fragments of a page are compressed one
 // after the other straight into the page's output slot, so no compaction pass is needed.
 // Shared memory: frag_cap + kFragPad bytes of fragment, then table_cap u16 entries, then mbarrier.
+// kLib: libsnappy's rules (option `rules`, 1 or 2), table sized per fragment up to table_cap.
+template <bool kLib = false>
 __global__ void __launch_bounds__(32)
 k_compress_pages(const u8* __restrict__ g_in, const u64* __restrict__ in_off,
                  const u32* __restrict__ in_size, u8* __restrict__ g_out,
                  const u64* __restrict__ out_off, u32* __restrict__ out_size, u32 frag_cap,
-                 u32 table_cap) {
+                 u32 table_cap, u32 lib_rules = 0) {
     extern __shared__ __align__(128) u8 smem[];
     u8* F = smem;
     u16* T = reinterpret_cast<u16*>(smem + frag_cap + kFragPad);
@@ -631,6 +637,7 @@ k_compress_pages(const u8* __restrict__ g_in, const u64* __restrict__ in_off,
     const u32 shift = 32 - (31 - __clz(entries));
 
     FragEmitter em{g_out + out_off[pg], 0, lane};
+    if (kLib) em.lit_short = 61;
     {   // varint header, src/varint.jl:46-69
         u32 v = total, k = 0;
         while (v >= 0x80) {
@@ -646,8 +653,17 @@ k_compress_pages(const u8* __restrict__ g_in, const u64* __restrict__ in_off,
         const u32 n = (total - s < kBlockSize) ? (total - s) : kBlockSize;
         __syncwarp();
         phase = load_fragment(F, bar, pin + s, n, lane, phase);
-        reset_table(T, shift, lane);
-        compress_fragment_serial(F, T, n, shift, em);
+        if (kLib) {  // GetHashTable: sized from this fragment's length
+            u32 e = 256;
+            while (e < table_cap && e < n) e <<= 1;
+            uint4* t4 = reinterpret_cast<uint4*>(T);
+            for (u32 i = lane; i < e / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            compress_fragment_serial<true>(F, T, n, lib_rules == 2u ? 17u : (u32)__clz((int)e) + 1u, em, e - 1u);
+        } else {
+            reset_table(T, shift, lane);
+            compress_fragment_serial(F, T, n, shift, em);
+        }
     }
     if (lane == 0) out_size[pg] = em.op;
 }

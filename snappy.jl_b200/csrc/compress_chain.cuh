@@ -56,8 +56,14 @@ __global__ void k_init_probe_offsets() {
     }
 }
 
-template <bool kSmemTable>
+// kLib: libsnappy emission rules instead of Snappy.jl's (option `rules`): ip_limit =
+// n - 15, a 60-byte literal keeps the one-byte header, the table is sized per fragment and the bucket of a hash
+// is ((w * mul) >> shift) & hmask (rules = 2: Google snappy >= 1.1.9, shift 17 and up to 32768 buckets).
+template <bool kSmemTable, bool kLib = false>
 struct Chain {
+    static constexpr u32 kLitShort = kLib ? 61u : 60u;   // literals below this take the one-byte header (:271)
+    static constexpr int kLimMargin = kLib ? 15 : 16;    // ip_limit = n - margin (:131)
+    u32 hmask;       // kLib only
     const u8* F;     // fragment bytes (global, >= 64 readable bytes past n)
     u16* T;          // hash table, position per hash, 0 == empty (global variant)
     u32 Ts;          // shared-space address of the table (shared variant)
@@ -66,7 +72,9 @@ struct Chain {
     int lim;
     u32 r_lit, r_cpy;  // lane k parks record k: (lit_from | ip << 16), (cand | M << 16)
 
-    __device__ __forceinline__ u32 hash(u32 w) const { return (w * kHashMul) >> shift; }
+    __device__ __forceinline__ u32 hash(u32 w) const {
+        return kLib ? (((w * kHashMul) >> shift) & hmask) : ((w * kHashMul) >> shift);
+    }
     __device__ __forceinline__ u32 tget(u32 h) const {
         if (kSmemTable) {
             u16 v;
@@ -123,7 +131,7 @@ struct Chain {
         const u32 lf = r_lit & 0xffffu, ll = mine ? ((r_lit >> 16) - lf) : 0u;
         const u32 off = (r_lit >> 16) - (r_cpy & 0xffffu), M = mine ? (r_cpy >> 16) : 0u;
         // :271-283 header bytes of the literal (a 60-byte literal already takes the long form)
-        const u32 lh = (ll == 0) ? 0u : (ll < 60 ? 1u : ((ll - 1) <= 0xffu ? 2u : ((ll - 1) <= 0xffffu ? 3u : 4u)));
+        const u32 lh = (ll == 0) ? 0u : (ll < kLitShort ? 1u : ((ll - 1) <= 0xffu ? 2u : ((ll - 1) <= 0xffffu ? 3u : 4u)));
         const u32 sz = lh + ll + copy_bytes(off, M);
         u32 incl = sz;
 #pragma unroll
@@ -139,7 +147,7 @@ struct Chain {
         }
         if (ll) {
             const u32 nm1 = ll - 1;
-            if (ll < 60) {
+            if (ll < kLitShort) {
                 out[pos] = (u8)(nm1 << 2);
             } else {
                 out[pos] = (u8)((59 + (lh - 1)) << 2);
@@ -241,9 +249,9 @@ struct Chain {
         if (nrec) flush();
         if (lit_from < n) {
             const u32 ll = n - lit_from, nm1 = ll - 1;
-            const u32 lh = ll < 60 ? 1u : (nm1 <= 0xffu ? 2u : (nm1 <= 0xffffu ? 3u : 4u));
+            const u32 lh = ll < kLitShort ? 1u : (nm1 <= 0xffu ? 2u : (nm1 <= 0xffffu ? 3u : 4u));
             if (lane == 0) {
-                if (ll < 60) {
+                if (ll < kLitShort) {
                     out[op] = (u8)(nm1 << 2);
                 } else {
                     out[op] = (u8)((59 + (lh - 1)) << 2);
@@ -266,7 +274,7 @@ struct Chain {
         op = 0;
         nrec = 0;
         r_lit = r_cpy = 0;
-        lim = (int)n - 16;  // ip_limit, :131
+        lim = (int)n - kLimMargin;  // ip_limit, :131
         asm volatile("" : "+r"(lim));
         u32 ip = 0, lit_from = 0;
         if (n >= kInputMargin) {

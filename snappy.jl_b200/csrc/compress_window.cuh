@@ -47,9 +47,9 @@ constexpr bool kFarAll = SB200_FAR_ALL != 0;
 #define SB200_M_BRANCHFREE 1
 #endif
 
-template <bool kSmemTable>
-struct Win : Chain<kSmemTable> {
-    using Base = Chain<kSmemTable>;
+template <bool kSmemTable, bool kLib = false>
+struct Win : Chain<kSmemTable, kLib> {
+    using Base = Chain<kSmemTable, kLib>;
     using Base::F;
     using Base::lane;
     using Base::lim;
@@ -150,7 +150,7 @@ struct Win : Chain<kSmemTable> {
         this->op = 0;
         this->nrec = 0;
         this->r_lit = this->r_cpy = 0;
-        lim = (int)n - 16;  // ip_limit, :131
+        lim = (int)n - Base::kLimMargin;  // ip_limit, :131
         u32 lit_from = 0;
         if (n >= kInputMargin) {
             bool arrival = false;  // round starts with a post-copy arrival at a (else: scanning)
@@ -366,20 +366,22 @@ struct Win : Chain<kSmemTable> {
 
 // Persistent warps, as k_compress_chain; each warp additionally owns `ring_bytes` of shared memory
 // (behind the tables for the shared-table variant).
-template <bool kSmemTable>
+// kLib (option `rules`): libsnappy's rules; lib_rules = 1: libsnappy <= 1.1.7 (hash >> shift, <= 16384 buckets),
+// 2: Google snappy >= 1.1.9 ((hash >> 17) & mask, <= 32768 buckets: 64 KiB tables); table size per fragment.
+template <bool kSmemTable, bool kLib = false>
 __global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
 k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                   const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
                   u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
                   const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes,
-                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1) {
+                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1, u32 lib_rules = 0) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarp = blockDim.x >> 5;
     const u32 gwarp = blockIdx.x * nwarp + warp;
-    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * kMaxTableEntries
-                        : gtables + (size_t)gwarp * kMaxTableEntries;
-    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * kMaxTableEntries * 2u : 0u) + warp * (ring_bytes + kRingMirror);
+    const u32 tab = kLib ? (lib_rules == 2u ? 2u * kMaxTableEntries : kMaxTableEntries) : kMaxTableEntries;
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * tab : gtables + (size_t)gwarp * tab;
+    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * tab * 2u : 0u) + warp * (ring_bytes + kRingMirror);
     const u32 lane = lane_id();
     for (;;) {
         if (reserve && *reinterpret_cast<volatile u32*>(counter) + reserve >= nfrag) break;
@@ -411,11 +413,17 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         }
         const u64 start = (u64)local * kBlockSize;
         const u32 n = (u32)((slen - start < kBlockSize) ? (slen - start) : kBlockSize);
-        const u32 entries = 1u << (32 - fshift);
+        u32 entries = 1u << (32 - fshift);
+        if (kLib) {  // GetHashTable: sized from THIS fragment's length
+            entries = 256;
+            while (entries < tab && entries < n) entries <<= 1;
+            fshift = lib_rules == 2u ? 17u : (u32)__clz((int)entries) + 1u;  // 32 - log2(entries)
+        }
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        Win<kSmemTable> ch;
+        Win<kSmemTable, kLib> ch;
+        ch.hmask = entries - 1u;
         ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;
         ch.Ts = kSmemTable ? smem_u32(T) : 0u;

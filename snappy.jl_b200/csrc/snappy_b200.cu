@@ -58,12 +58,15 @@ struct Options {
     int l2_reserve = 1;         // global-table warps stop pulling when fewer than l2_reserve x (smem warps) fragments remain
     int wide = 0;               // 2 or 4: warps per fragment of the wide window kernel (compress_wide.cuh); 0 = off
     int l2_persist = 0;         // 1 = pin the global hash tables in L2 (access policy window on the side stream)
+    int rules = 0;              // emission rules: 0 = Snappy.jl (the reference, default), 1 = libsnappy <= 1.1.7,
+                                // 2 = Google snappy >= 1.1.9 (byte-identical to pyarrow's bundled codec)
     int window = 1;             // 1 = window-parallel kernel (compress_window.cuh), 0 = step-wise chain kernel
     int ring_smem = 2048;       // history ring per shared-table warp (bytes, power of two >= 1024)
     int ring_l2 = 1024;         // history ring per global-table warp
     int spec_smem = 32;         // copy end positions pre-probed per step by shared-table warps (1..32)
     int spec_l2 = 16;           // same for global-table warps (each probing lane costs an L1tex wavefront)
     int l2_chains = 14;         // warps per CTA of the global-table (L2) kernel, <= 20 (window kernel; <= 14 for the chain kernel)
+    int l2_chains_big = 14;     // the same under rules = 2 (64 KiB tables; measured 4: 25.1, 8: 20.3, 10: 19.1, 14: 17.5 ms/GiB)
     int l2_ctas = 1;            // CTAs per SM of that kernel (1..3): l2_ctas x l2_chains extra chains per SM
     int decode_variant = 0;     // 0 = default, 1 = force exact serial decoder
     int decode_occupancy = 12;  // CTAs (of 4 warps) per SM the indexed decoder is compiled for: 8, 10 or 12
@@ -121,6 +124,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
     else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
     else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
+    else if (!strcmp(name, "l2_chains_big")) g_ctx.opt.l2_chains_big = value < 0 ? 0 : (value > 20 ? 20 : value);
     else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
     else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
     else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
@@ -136,6 +140,7 @@ void apply_option(const char* name, int value) {
         const u32 v = (u32)value;
         cudaMemcpyToSymbol(g_dbg_skip_emit, &v, 4);
     }
+    else if (!strcmp(name, "rules")) g_ctx.opt.rules = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
     else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
@@ -189,8 +194,10 @@ int ctx_init_locked(int device) {
                 c.l2_persist_max >> 20, c.l2_window_max >> 20);
     CU(cudaFuncSetAttribute(k_compress_fragments_serial, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompressSmemBytes));
-    CU(cudaFuncSetAttribute(k_compress_pages, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(k_compress_pages<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompressSmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_pages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kCompressSmemBytes + kMaxTableEntries * 2)));
     CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompress2SmemBytes));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -203,6 +210,12 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
@@ -322,17 +335,25 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     u32* counter = (u32*)((u8*)c.result.p + 64);
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
-    const u32 wa = (u32)c.opt.smem_chains;
+    // rules != 0 (libsnappy's emission rules): always the window kernel, compiled with kLib; rules = 2 has
+    // 64 KiB tables, so 3 shared-table warps per SM (and l2_chains_big global-table warps)
+    const u32 rules = (u32)c.opt.rules;
+    const u32 tab_bytes = (rules == 2 ? 2u : 1u) * kMaxTableEntries * 2u;
+    u32 wa = (u32)c.opt.smem_chains;
     // (the step-wise chain kernel is compiled for <= 14 warps per CTA)
-    const u32 wb = (!c.opt.window && c.opt.l2_chains > 14) ? 14u : (u32)c.opt.l2_chains;
+    u32 wb = (!c.opt.window && !rules && c.opt.l2_chains > 14) ? 14u : (u32)c.opt.l2_chains;
+    if (rules == 2) {
+        if (wa > 3) wa = 3;
+        wb = (u32)c.opt.l2_chains_big;
+    }
     u32 ctas_a = wa ? (nfrag + wa - 1) / wa : 0u;  // smem_chains == 0: global-table warps only (profiling)
     if (ctas_a > (u32)c.sm_count) ctas_a = (u32)c.sm_count;
     const u32 warps_a = ctas_a * wa;
     const u32 reserve = (u32)c.opt.l2_reserve * warps_a;
     const u32 ctas_b = (wb && (nfrag > warps_a + reserve || !wa)) ? (u32)(c.sm_count * c.opt.l2_ctas) : 0u;
-    if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * kMaxTableEntries * 2));
+    if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * tab_bytes));
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
-    if (c.opt.wide == 2 || c.opt.wide == 4) {  // kW warps per fragment, shared tables only
+    if (!rules && (c.opt.wide == 2 || c.opt.wide == 4)) {  // kW warps per fragment, shared tables only
         const u32 chains = (u32)c.opt.smem_chains, ra = (u32)c.opt.ring_smem;
         u32 ctas = (nfrag + chains - 1) / chains;
         if (ctas > (u32)c.sm_count) ctas = (u32)c.sm_count;
@@ -345,10 +366,14 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         *launches += 1;
         return SNAPPY_B200_OK;
     }
-    const bool window = c.opt.window != 0;
+    const bool window = c.opt.window != 0 || rules != 0;
     const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
     if (ctas_a) {
-        if (window)
+        if (rules)
+            k_compress_window<true, true><<<ctas_a, wa * 32, (size_t)wa * (tab_bytes + ra + kRingMirror), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules);
+        else if (window)
             k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
                 ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
@@ -374,7 +399,12 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             CU(cudaStreamSetAttribute(c.side, cudaStreamAttributeAccessPolicyWindow, &av));
         }
-        if (window)
+        if (rules)
+            k_compress_window<false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
+                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
+                gate ? gate->div : 1u, rules);
+        else if (window)
             k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
@@ -468,7 +498,7 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
         *total_out = ((volatile u64*)h_tot)[nchunks - 1];
         return SNAPPY_B200_OK;
     }
-    if (c.opt.compress_variant == 0) {
+    if (c.opt.compress_variant == 0 || c.opt.rules) {
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
         int rc = launch_chain_kernels(c, d_in, shard_len, shift, scratch, sizes, st, &launches);
         if (rc != SNAPPY_B200_OK) return rc;
@@ -1343,12 +1373,17 @@ int snappy_b200_compress_batched_device(const uint8_t* d_in, const uint64_t* d_i
     const u32 max_size = h[0];
     u32 frag_cap = max_size < kBlockSize ? ((max_size + 15) & ~15u) : kBlockSize;
     if (frag_cap < 16) frag_cap = 16;
+    const u32 rules = (u32)c.opt.rules;
     u32 entries = 256;
-    while (entries < kMaxTableEntries && entries < max_size) entries <<= 1;
+    while (entries < (rules == 2 ? 2u : 1u) * kMaxTableEntries && entries < max_size) entries <<= 1;
     const size_t smem = (size_t)frag_cap + kFragPad + (size_t)entries * 2 + 16;
     if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
-    k_compress_pages<<<(unsigned)count, 32, smem, st>>>(d_in, d_in_offsets, d_in_sizes, d_out,
-                                                        d_out_offsets, d_out_sizes, frag_cap, entries);
+    if (rules)
+        k_compress_pages<true><<<(unsigned)count, 32, smem, st>>>(d_in, d_in_offsets, d_in_sizes, d_out, d_out_offsets,
+                                                                  d_out_sizes, frag_cap, entries, rules);
+    else
+        k_compress_pages<false><<<(unsigned)count, 32, smem, st>>>(d_in, d_in_offsets, d_in_sizes, d_out,
+                                                                   d_out_offsets, d_out_sizes, frag_cap, entries);
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[1], st));
         c.ev_pending[0] = true;

@@ -122,6 +122,10 @@ function unpack_index(sidecar::Vector{UInt8})
     end
 end
 
+# Which compressor's bytes `compress` reproduces (include/snappy_b200.h, option "rules"): 0 = Snappy.jl
+# (src/internal.jl, the default), 1 = libsnappy <= 1.1.7, 2 = Google snappy >= 1.1.9.
+set_rules(rules::Integer) = ccall((:snappy_b200_set_option, LIB), Cvoid, (Cstring, Cint), "rules", rules)
+
 # Optional: pick the device / create the context up front (otherwise lazy on first call).
 init(device::Integer = -1) = _check(ccall((:snappy_b200_init, LIB), Cint, (Cint,), device))
 
