@@ -70,3 +70,21 @@ def test_parquet_pages_compress_on_gpu(oracle):
     assert len(ours) == len(raw_pages)
     for a, b in zip(ours, raw_pages):
         assert a == oracle.compress(b)
+
+
+@pytest.mark.gpu
+def test_parquet_page_bodies_are_byte_identical_to_the_writer_under_google_rules(snappy):
+    """rules = 2: recompressing the decoded pages gives back the very bytes pyarrow's Google snappy
+    wrote into the file."""
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("1.0", 4096, rows=30_000)
+    pages, out, offs = pp.uncompress_pages(f)
+    sel = [(p, o) for p, o in zip(pages, offs) if o >= 0]
+    try:
+        snappy.set_rules(2)
+        ours = pp.compress_pages([out[o: o + p["uncompressed"]].tobytes() for p, o in sel])
+    finally:
+        snappy.set_rules(0)
+    assert len(ours) > 50
+    for body, (p, _) in zip(ours, sel):
+        assert body == bytes(f[p["stream"]: p["stream"] + p["compressed"]])
