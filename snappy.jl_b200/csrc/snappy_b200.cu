@@ -95,6 +95,7 @@ struct Context {
     // staging for the host-buffer API
     DevBuf stage_in, stage_out;
     void* pinned = nullptr;  // small pinned readback area (4 KiB)
+    void* pinned_zero = nullptr;  // kTailPad zero bytes (pinned): pads go up through the copy engine
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[2] = {0.f, 0.f};
     int last_launches[2] = {0, 0};
@@ -235,6 +236,8 @@ int ctx_init_locked(int device) {
     CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CU(cudaMallocHost(&c.pinned, 4096));
+    CU(cudaMallocHost(&c.pinned_zero, kTailPad));
+    memset(c.pinned_zero, 0, kTailPad);
     for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
     CU(c.result.ensure(256));
     c.ready = true;
@@ -802,10 +805,11 @@ void snappy_b200_shutdown(void) {
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
     for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
-                      &c.parse_c, &c.index, &c.stage_in, &c.stage_out})
+                      &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
-    c.pinned = nullptr;
+    if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
+    c.pinned = c.pinned_zero = nullptr;
     for (auto& ev : c.ev) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
@@ -906,16 +910,20 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
     CU(cudaEventRecord(c.ev_in[0], c.s_comp));
     // The copies are enqueued BEFORE the kernels that wait for them: streams can share a hardware queue
     // (CUDA_DEVICE_MAX_CONNECTIONS), and a copy queued behind a kernel that waits for it would never run.
-    // input: chunk, then the count of resident fragments (the tail copy goes in before the last count)
+    // input: chunk, then the count of resident fragments
     CU(cudaStreamWaitEvent(c.s_h2d, c.ev_in[0], 0));
+    {   // padded copy of the last fragment, straight from the host buffer and first of all: nothing on this
+        // stream may need an SM (a device-to-device copy or a memset can be a kernel) once the persistent
+        // kernels sit on every SM waiting for the counts below
+        const u64 tail_start = (u64)(nfrag - 1) * kBlockSize;
+        const size_t tail_len = n - tail_start;
+        CU(cudaMemcpyAsync(c.tail.p, in + tail_start, tail_len, cudaMemcpyHostToDevice, c.s_h2d));
+        CU(cudaMemcpyAsync((u8*)c.tail.p + tail_len, c.pinned_zero, kTailPad, cudaMemcpyHostToDevice, c.s_h2d));
+    }
     for (int i = 0; i < nchunks; i++) {
         const size_t off = (size_t)i * cf * kBlockSize;
         const size_t len = (n - off < cf * kBlockSize) ? (n - off) : cf * kBlockSize;
         CU(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c.s_h2d));
-        if (i == nchunks - 1) {
-            int rc = stage_tail(c, d_in, n, 0, c.s_h2d);
-            if (rc != SNAPPY_B200_OK) return rc;
-        }
         h_ready[i] = (i == nchunks - 1) ? nfrag : (u32)((size_t)(i + 1) * cf);
         CU(cudaMemcpyAsync(d_ready, h_ready + i, 4, cudaMemcpyHostToDevice, c.s_h2d));
     }
