@@ -158,3 +158,11 @@ def test_gpu_rules_batched_pages(snappy, oracle, rules_mode, rules):
     out, oo, os_ = dev.compress_batched_device(to_dev(one), to_dev(np.zeros(1, dtype=np.int64)),
                                                to_dev(np.array([one.size], dtype=np.int32)))
     assert out.cpu().numpy()[: int(os_.cpu()[0])].tobytes() == oracle.compress_rules(one, rules)
+
+
+def test_set_rules_validates_and_needs_no_device(snappy):
+    """the switch is host state: it can be set before any device exists, and rejects unknown rule sets"""
+    snappy.set_rules(2)
+    snappy.set_rules(0)
+    with pytest.raises(ValueError):
+        snappy.set_rules(3)
