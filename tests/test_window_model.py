@@ -33,3 +33,16 @@ def test_window_model_matches_oracle(model, ww):
     assert len(lines) == len(FILES)
     for l in lines:
         assert " 0 mismatches" in l, l
+
+
+@pytest.mark.parametrize("rules", ["1", "2"])
+def test_window_model_matches_oracle_under_google_rules(model, rules):
+    """the kLib instantiations: ip_limit n - 15, short 60-byte literal, per-fragment table, and for
+    rules 2 the masked 15-bit bucket with up to 32768 entries -- against sjo_compress_fragment_rules"""
+    env = dict(os.environ, RULES=rules)
+    out = subprocess.run([model] + [os.path.join(DATA, f) for f in FILES], env=env, capture_output=True,
+                         text=True, check=True).stdout
+    lines = [l for l in out.splitlines() if "fragments" in l]
+    assert len(lines) == len(FILES)
+    for l in lines:
+        assert " 0 mismatches" in l, l

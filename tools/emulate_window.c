@@ -17,15 +17,20 @@
 
 static inline uint32_t ld32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
-typedef struct { const uint8_t *F; long n, lim; uint32_t shift; uint16_t T[16384]; uint8_t *out, *op;
+/* RULES (env): 0 = Snappy.jl, 1 = libsnappy <= 1.1.7, 2 = Google snappy >= 1.1.9 (the kernels' kLib instantiations,
+ * DESIGN.md 4c): ip_limit margin, the 60-byte literal, the bucket function and the table size per fragment */
+static int RULES = 0;
+typedef struct { const uint8_t *F; long n, lim; uint32_t shift, hmask; uint16_t T[32768]; uint8_t *out, *op;
                  long rounds, hops, slow, generic; } Frag;
 
-static uint32_t hashw(const Frag *f, uint32_t w) { return (w * 0x1e35a7bdu) >> f->shift; }
+static uint32_t hashw(const Frag *f, uint32_t w) {
+    return RULES == 2 ? (((w * 0x1e35a7bdu) >> 17) & f->hmask) : ((w * 0x1e35a7bdu) >> f->shift);
+}
 
 static void emit_literal(Frag *f, long from, long to) {
     long len = to - from; if (len <= 0) return;
     uint32_t n = (uint32_t)(len - 1); uint8_t *op = f->op;
-    if (len < 60) *op++ = (uint8_t)(n << 2);
+    if (len < (RULES ? 61 : 60)) *op++ = (uint8_t)(n << 2);
     else { uint8_t *base = op; int count = 0; while (n > 0) { *++op = (uint8_t)n; n >>= 8; count++; } *base = (uint8_t)((59 + count) << 2); op++; }
     memcpy(op, f->F + from, (size_t)len); f->op = op + len;
 }
@@ -51,7 +56,7 @@ enum { ARR = 0, SCAN = 1 };
  * rounds but cost more instructions than it saved on the GPU: 28.2 vs 27.0 ms); CAP equal bytes go to the whole-warp extension */
 static uint32_t CAP = 16;
 static size_t compress_fragment_window(Frag *f) {
-    const uint8_t *F = f->F; const long n = f->n, lim = n - 16; f->lim = lim; f->op = f->out;
+    const uint8_t *F = f->F; const long n = f->n, lim = n - (RULES ? 15 : 16); f->lim = lim; f->op = f->out;
     memset(f->T, 0, sizeof f->T);
     long lit_from = 0;
     if (n >= 15) {
@@ -151,7 +156,7 @@ static size_t compress_fragment_window(Frag *f) {
 static int WW = 4;
 static long st_windows, st_stale_lanes, st_entered;
 static size_t compress_fragment_multi(Frag *f) {
-    const uint8_t *F = f->F; const long n = f->n, lim = n - 16; f->lim = lim; f->op = f->out;
+    const uint8_t *F = f->F; const long n = f->n, lim = n - (RULES ? 15 : 16); f->lim = lim; f->op = f->out;
     memset(f->T, 0, sizeof f->T);
     long lit_from = 0;
     if (n >= 15) {
@@ -257,6 +262,7 @@ int main(int argc, char **argv) {
     init_po();
     if (getenv("WW")) WW = atoi(getenv("WW"));
     if (getenv("CAP")) CAP = (uint32_t)atoi(getenv("CAP"));
+    if (getenv("RULES")) RULES = atoi(getenv("RULES"));
     for (int ai = 1; ai < argc; ai++) {
         FILE *fp = fopen(argv[ai], "rb"); if (!fp) { perror(argv[ai]); return 1; }
         fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
@@ -264,15 +270,21 @@ int main(int argc, char **argv) {
         uint32_t entries = sjo_hashtable_entries((uint64_t)sz);
         uint32_t shift = 32; for (uint32_t e = entries; e > 1; e >>= 1) shift--;
         long nfrag = (sz + 65535) / 65536, bad = 0; Frag *f = calloc(1, sizeof(Frag)); f->shift = shift;
-        uint8_t *o1 = malloc(80000), *o2 = malloc(80000); uint16_t *tab = malloc(16384 * 2);
+        uint8_t *o1 = malloc(80000), *o2 = malloc(80000); uint16_t *tab = malloc(32768 * 2);
         for (long fr = 0; fr < nfrag; fr++) {
             long n = sz - fr * 65536 < 65536 ? sz - fr * 65536 : 65536;
             /* the kernel reads past the fragment end only into readable memory; values there must not matter */
             uint8_t *frag = calloc((size_t)n + 256, 1); memcpy(frag, buf + fr * 65536, (size_t)n); memset(frag + n, 0xA5, 200);
             f->F = frag; f->n = n; f->out = o1;
+            if (RULES) {  /* GetHashTable: per fragment, up to 16384 (rules 1) or 32768 (rules 2) buckets */
+                entries = 256; while (entries < (RULES == 2 ? 32768u : 16384u) && entries < (uint32_t)n) entries <<= 1;
+                f->shift = 32; for (uint32_t e = entries; e > 1; e >>= 1) f->shift--;
+            }
+            f->hmask = entries - 1;
             size_t c1 = getenv("WW") ? compress_fragment_multi(f) : compress_fragment_window(f);
-            memset(tab, 0xff, entries * 2);
-            size_t c2 = sjo_compress_fragment(frag, (size_t)n, o2, tab, entries);
+            size_t c2;
+            if (RULES) { memset(tab, 0, entries * 2); c2 = sjo_compress_fragment_rules(frag, (size_t)n, o2, tab, entries, RULES); }
+            else { memset(tab, 0xff, entries * 2); c2 = sjo_compress_fragment(frag, (size_t)n, o2, tab, entries); }
             if (c1 != c2 || memcmp(o1, o2, c1)) { bad++; if (bad < 4) fprintf(stderr, "%s: fragment %ld differs (%zu vs %zu)\n", argv[ai], fr, c1, c2); }
             free(frag);
         }
