@@ -46,3 +46,15 @@ def test_window_model_matches_oracle_under_google_rules(model, rules):
     assert len(lines) == len(FILES)
     for l in lines:
         assert " 0 mismatches" in l, l
+
+
+def test_window_model_is_exact_for_a_64_wide_window(tmp_path):
+    """two positions per lane (the round-2 direction in DESIGN.md 9): same bytes as the oracle, ~35 % fewer rounds"""
+    exe = str(tmp_path / "emulate_window64")
+    subprocess.check_call(["gcc", "-O2", "-DW=64", "-o", exe, os.path.join(ROOT, "tools", "emulate_window.c"),
+                           os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    out = subprocess.run([exe] + [os.path.join(DATA, f) for f in FILES], capture_output=True, text=True, check=True).stdout
+    lines = [l for l in out.splitlines() if "fragments" in l]
+    assert len(lines) == len(FILES)
+    for l in lines:
+        assert " 0 mismatches" in l, l

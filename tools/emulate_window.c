@@ -55,6 +55,17 @@ enum { ARR = 0, SCAN = 1 };
 /* bytes compared per lane (the kernels use 16; CAP=32 models "16 more for lanes that match all 16", which saved
  * rounds but cost more instructions than it saved on the GPU: 28.2 vs 27.0 ms); CAP equal bytes go to the whole-warp extension */
 static uint32_t CAP = 16;
+/* STATS=1: why rounds end and how far each kind advances the window start (guides what to optimise) */
+enum { E_LEAVE, E_SCAN_DUP, E_SCAN_LIMIT, E_ARR_DUP, E_ARR_BEYOND, E_SLOW, E_FIN, E_KINDS };
+static const char *const E_NAME[E_KINDS] = {"scan covers window", "scan stops at untrusted lane", "scan reaches probe 32",
+                                            "arrival at untrusted lane", "copy lands beyond window", "copy >= 16 bytes", "fragment end"};
+static long e_count[E_KINDS], e_adv[E_KINDS];
+/* W: positions evaluated per round (compile with -DW=64 to model two positions per lane; the kernels use 32).
+ * Measured with this model (rounds per fragment, W = 32 -> 48 -> 64): dictionary class 1951 -> 1502 -> 1272, text
+ * class 2014 -> 1543 -> 1337, alice29 1532 -> 1110 -> 911, html 976 -> 864 -> 834, records class 604 -> 603 (long copies). */
+#ifndef W
+#define W 32
+#endif
 static size_t compress_fragment_window(Frag *f) {
     const uint8_t *F = f->F; const long n = f->n, lim = n - (RULES ? 15 : 16); f->lim = lim; f->op = f->out;
     memset(f->T, 0, sizeof f->T);
@@ -81,9 +92,9 @@ static size_t compress_fragment_window(Frag *f) {
             }
             f->rounds++;
             /* ---- lane evaluation against the table as of the round start */
-            uint32_t H[32], t[32], m[32]; int V[32], dup[32];
+            uint32_t H[W], t[W], m[W]; int V[W], dup[W];
             if (mode == ARR) f->T[hashw(f, ld32(F + a - 1))] = (uint16_t)(a - 1); /* :233 */
-            for (int l = 0; l < 32; l++) {
+            for (int l = 0; l < W; l++) {
                 long q = a + l; V[l] = q < lim;
                 H[l] = V[l] ? hashw(f, ld32(F + q)) : (0x80000000u | (uint32_t)l);
                 t[l] = V[l] ? f->T[H[l]] : 0; dup[l] = 0;
@@ -91,56 +102,58 @@ static size_t compress_fragment_window(Frag *f) {
                 uint32_t k = 0; if (V[l]) while (k < CAP && q + k < n && F[t[l] + k] == F[q + k]) k++;
                 m[l] = k;
             }
-            uint32_t ins = 0; int fin = 0, next_mode = -1; long next_a = 0;
+            uint64_t ins = 0; int fin = 0, next_mode = -1; long next_a = 0;
             long slow_ip = -1, slow_cand = 0;
-            int l = 0; int scanning = (mode == SCAN);
+            int l = 0; int scanning = (mode == SCAN); int ek = E_FIN;
             for (;;) {
                 f->hops++;
                 if (!scanning) { /* arrival at lane l: :228-238 */
-                    if (l > 0 && dup[l]) { next_mode = ARR; next_a = a + l; break; }
-                    if (l > 0) ins |= 1u << (l - 1);
-                    ins |= 1u << l;
+                    if (l > 0 && dup[l]) { next_mode = ARR; next_a = a + l; ek = E_ARR_DUP; break; }
+                    if (l > 0) ins |= 1ull << (l - 1);
+                    ins |= 1ull << l;
                     if (m[l] >= 4) {
                         if (m[l] == CAP) { slow_ip = a + l; slow_cand = t[l]; break; }
                         record(f, lit_from, a + l, t[l], m[l]); lit_from = a + l + m[l];
                         long tgt = l + m[l];
                         if (a + tgt >= lim) { fin = 1; break; }
-                        if (tgt >= 32) { next_mode = ARR; next_a = a + tgt; break; }
+                        if (tgt >= W) { next_mode = ARR; next_a = a + tgt; ek = E_ARR_BEYOND; break; }
                         l = (int)tgt; continue;
                     }
                     scanning = 1; scan_s = a + l + 1; l = l + 1; continue;
                 }
                 /* scanning from lane l: :167-194 */
                 int e = l;
-                for (; e < 32; e++) {
+                for (; e < W; e++) {
                     if (!V[e]) break;
                     if (a + e - scan_s >= 32) break;
                     if (dup[e] && e > 0) break;
                     if (m[e] >= 4) break;
-                    ins |= 1u << e;
+                    ins |= 1ull << e;
                 }
-                if (e >= 32) { next_mode = SCAN; next_a = a + 32; break; }
+                if (e >= W) { next_mode = SCAN; next_a = a + W; ek = E_LEAVE; break; }
                 if (!V[e]) { fin = 1; break; }
-                if (a + e - scan_s >= 32) { next_mode = SCAN; next_a = a + e; break; }
-                if (dup[e] && e > 0) { next_mode = SCAN; next_a = a + e; break; }
-                ins |= 1u << e; /* hit */
+                if (a + e - scan_s >= 32) { next_mode = SCAN; next_a = a + e; ek = E_SCAN_LIMIT; break; }
+                if (dup[e] && e > 0) { next_mode = SCAN; next_a = a + e; ek = E_SCAN_DUP; break; }
+                ins |= 1ull << e; /* hit */
                 if (m[e] == CAP) { slow_ip = a + e; slow_cand = t[e]; break; }
                 record(f, lit_from, a + e, t[e], m[e]); lit_from = a + e + m[e];
                 long tgt = e + m[e];
                 if (a + tgt >= lim) { fin = 1; break; }
-                if (tgt >= 32) { next_mode = ARR; next_a = a + tgt; break; }
+                if (tgt >= W) { next_mode = ARR; next_a = a + tgt; ek = E_ARR_BEYOND; break; }
                 scanning = 0; l = (int)tgt;
             }
             /* ---- commit the inserts of the path; on equal hashes the later position wins (:191) */
-            for (int k = 0; k < 32; k++) if (ins >> k & 1) f->T[hashw(f, ld32(F + a + k))] = (uint16_t)(a + k);
+            for (int k = 0; k < W; k++) if (ins >> k & 1) f->T[hashw(f, ld32(F + a + k))] = (uint16_t)(a + k);
             if (slow_ip >= 0) { /* long copy: full-length compare */
                 f->slow++;
                 long M = CAP; while (slow_ip + M < n && F[slow_cand + M] == F[slow_ip + M]) M++;
                 record(f, lit_from, slow_ip, slow_cand, M); lit_from = slow_ip + M;
+                e_count[E_SLOW]++; e_adv[E_SLOW] += lit_from - a;
                 if (lit_from >= lim) break;
                 mode = ARR; a = lit_from; continue;
             }
-            if (fin) break;
+            if (fin) { e_count[E_FIN]++; break; }
+            e_count[ek]++; e_adv[ek] += next_a - a;
             mode = next_mode; a = next_a;
         }
     }
@@ -287,6 +300,13 @@ int main(int argc, char **argv) {
             else { memset(tab, 0xff, entries * 2); c2 = sjo_compress_fragment(frag, (size_t)n, o2, tab, entries); }
             if (c1 != c2 || memcmp(o1, o2, c1)) { bad++; if (bad < 4) fprintf(stderr, "%s: fragment %ld differs (%zu vs %zu)\n", argv[ai], fr, c1, c2); }
             free(frag);
+        }
+        if (getenv("STATS") && !getenv("WW")) {
+            long tot = 0; for (int k = 0; k < E_KINDS; k++) tot += e_count[k];
+            for (int k = 0; k < E_KINDS; k++) {
+                printf("    %-30s %5.1f %% of rounds, advance %5.1f bytes\n", E_NAME[k], 100.0 * e_count[k] / (tot ? tot : 1), (double)e_adv[k] / (e_count[k] ? e_count[k] : 1));
+                e_count[k] = e_adv[k] = 0;
+            }
         }
         printf("%s: %ld fragments, %ld mismatches, rounds/frag %.0f hops/round %.2f slow/frag %.0f generic/frag %.0f windows entered/round %.2f stale lanes/window %.2f\n", argv[ai], nfrag, bad,
                (double)f->rounds / nfrag, (double)f->hops / (f->rounds ? f->rounds : 1), (double)f->slow / nfrag, (double)f->generic / nfrag, (double)st_entered / (f->rounds ? f->rounds : 1), (double)st_stale_lanes / (st_windows ? st_windows : 1)); st_entered = st_windows = st_stale_lanes = 0;
