@@ -58,3 +58,18 @@ def test_window_model_is_exact_for_a_64_wide_window(tmp_path):
     assert len(lines) == len(FILES)
     for l in lines:
         assert " 0 mismatches" in l, l
+
+
+@pytest.mark.parametrize("width", ["32", "64"])
+def test_window_model_variants_stay_exact(tmp_path, width):
+    """SLOWCONT / PRECISE: candidate refinements of the round (tools/emulate_window.c), exact by construction"""
+    exe = str(tmp_path / "emulate_window_v")
+    subprocess.check_call(["gcc", "-O2", "-DW=" + width, "-o", exe, os.path.join(ROOT, "tools", "emulate_window.c"),
+                           os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    env = dict(os.environ, SLOWCONT="1", PRECISE="1")
+    out = subprocess.run([exe] + [os.path.join(DATA, f) for f in FILES], env=env, capture_output=True, text=True,
+                         check=True).stdout
+    lines = [l for l in out.splitlines() if "fragments" in l]
+    assert len(lines) == len(FILES)
+    for l in lines:
+        assert " 0 mismatches" in l, l

@@ -60,6 +60,12 @@ enum { E_LEAVE, E_SCAN_DUP, E_SCAN_LIMIT, E_ARR_DUP, E_ARR_BEYOND, E_SLOW, E_FIN
 static const char *const E_NAME[E_KINDS] = {"scan covers window", "scan stops at untrusted lane", "scan reaches probe 32",
                                             "arrival at untrusted lane", "copy lands beyond window", "copy >= 16 bytes", "fragment end"};
 static long e_count[E_KINDS], e_adv[E_KINDS];
+/* variants of the round that are NOT in the kernels (yet); all exact, measured here in rounds per fragment:
+ *   SLOWCONT=1  a copy of >= 16 bytes is extended inside the hop loop and the chain goes on in the same window when
+ *               it lands there (W=32: dictionary 1951 -> 1835, html 976 -> 900; W=64: 1272 -> 1084, 834 -> 654)
+ *   PRECISE=1   a lane with an equal-hash lower lane is distrusted only if that lane was inserted on the path
+ *               (W=32: -0.3 .. -2 %; W=64: text 1337 -> 1255) */
+static int SLOWCONT = 0, PRECISE = 0;
 /* W: positions evaluated per round (compile with -DW=64 to model two positions per lane; the kernels use 32).
  * Measured with this model (rounds per fragment, W = 32 -> 48 -> 64): dictionary class 1951 -> 1502 -> 1272, text
  * class 2014 -> 1543 -> 1337, alice29 1532 -> 1110 -> 911, html 976 -> 864 -> 834, records class 604 -> 603 (long copies). */
@@ -108,11 +114,24 @@ static size_t compress_fragment_window(Frag *f) {
             for (;;) {
                 f->hops++;
                 if (!scanning) { /* arrival at lane l: :228-238 */
-                    if (l > 0 && dup[l]) { next_mode = ARR; next_a = a + l; ek = E_ARR_DUP; break; }
+                    if (l > 0 && dup[l]) {
+                        int stale = 1;
+                        if (PRECISE) { stale = 0; for (int j = 0; j < l; j++) if (H[j] == H[l] && ((ins >> j & 1) || j == l - 1)) stale = 1; }
+                        if (stale) { next_mode = ARR; next_a = a + l; ek = E_ARR_DUP; break; }
+                    }
                     if (l > 0) ins |= 1ull << (l - 1);
                     ins |= 1ull << l;
                     if (m[l] >= 4) {
-                        if (m[l] == CAP) { slow_ip = a + l; slow_cand = t[l]; break; }
+                        if (m[l] == CAP) {
+                            if (!SLOWCONT) { slow_ip = a + l; slow_cand = t[l]; break; }
+                            long M = CAP; while (a + l + M < n && F[t[l] + M] == F[a + l + M]) M++;
+                            f->slow++;
+                            record(f, lit_from, a + l, t[l], M); lit_from = a + l + M;
+                            long tgt = l + M;
+                            if (a + tgt >= lim) { fin = 1; break; }
+                            if (tgt >= W) { next_mode = ARR; next_a = a + tgt; ek = E_SLOW; break; }
+                            l = (int)tgt; continue;
+                        }
                         record(f, lit_from, a + l, t[l], m[l]); lit_from = a + l + m[l];
                         long tgt = l + m[l];
                         if (a + tgt >= lim) { fin = 1; break; }
@@ -126,15 +145,31 @@ static size_t compress_fragment_window(Frag *f) {
                 for (; e < W; e++) {
                     if (!V[e]) break;
                     if (a + e - scan_s >= 32) break;
-                    if (dup[e] && e > 0) break;
+                    if (dup[e] && e > 0) {
+                        int stale = 1;
+                        if (PRECISE) { stale = 0; for (int j = 0; j < e; j++) if (H[j] == H[e] && (ins >> j & 1)) stale = 1; }
+                        if (stale) break;
+                    }
                     if (m[e] >= 4) break;
                     ins |= 1ull << e;
                 }
                 if (e >= W) { next_mode = SCAN; next_a = a + W; ek = E_LEAVE; break; }
                 if (!V[e]) { fin = 1; break; }
                 if (a + e - scan_s >= 32) { next_mode = SCAN; next_a = a + e; ek = E_SCAN_LIMIT; break; }
-                if (dup[e] && e > 0) { next_mode = SCAN; next_a = a + e; ek = E_SCAN_DUP; break; }
+                {   int stale = dup[e] && e > 0;
+                    if (stale && PRECISE) { stale = 0; for (int j = 0; j < e; j++) if (H[j] == H[e] && (ins >> j & 1)) stale = 1; }
+                    if (stale) { next_mode = SCAN; next_a = a + e; ek = E_SCAN_DUP; break; }
+                }
                 ins |= 1ull << e; /* hit */
+                if (m[e] == CAP && SLOWCONT) {
+                    long M = CAP; while (a + e + M < n && F[t[e] + M] == F[a + e + M]) M++;
+                    f->slow++;
+                    record(f, lit_from, a + e, t[e], M); lit_from = a + e + M;
+                    long tgt = e + M;
+                    if (a + tgt >= lim) { fin = 1; break; }
+                    if (tgt >= W) { next_mode = ARR; next_a = a + tgt; ek = E_SLOW; break; }
+                    scanning = 0; l = (int)tgt; continue;
+                }
                 if (m[e] == CAP) { slow_ip = a + e; slow_cand = t[e]; break; }
                 record(f, lit_from, a + e, t[e], m[e]); lit_from = a + e + m[e];
                 long tgt = e + m[e];
@@ -276,6 +311,8 @@ int main(int argc, char **argv) {
     if (getenv("WW")) WW = atoi(getenv("WW"));
     if (getenv("CAP")) CAP = (uint32_t)atoi(getenv("CAP"));
     if (getenv("RULES")) RULES = atoi(getenv("RULES"));
+    if (getenv("SLOWCONT")) SLOWCONT = atoi(getenv("SLOWCONT"));
+    if (getenv("PRECISE")) PRECISE = atoi(getenv("PRECISE"));
     for (int ai = 1; ai < argc; ai++) {
         FILE *fp = fopen(argv[ai], "rb"); if (!fp) { perror(argv[ai]); return 1; }
         fseek(fp, 0, SEEK_END); long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
