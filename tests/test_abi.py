@@ -121,3 +121,43 @@ def test_index_sidecar_roundtrip_and_rejects(snappy):
         snappy.unpack_index(snappy.pack_index(np.array([1, 9, 20], dtype=np.uint64), 65536))
     with pytest.raises(snappy.SnappyError):                 # decreasing offsets
         snappy.pack_index(np.array([5, 4], dtype=np.uint64), 10)
+
+
+def test_index_sidecar_fuzz_with_valid_checksum(snappy):
+    """the sidecar comes from outside: mutated blobs whose checksum has been fixed up (so the parser goes all the
+    way in) either unpack to exactly what a re-pack reproduces or are rejected -- never a crash or a wrong length"""
+    def fnv1a(b):
+        h = 2166136261
+        for x in b:
+            h = ((h ^ x) * 16777619) & 0xFFFFFFFF
+        return h
+
+    rng = np.random.default_rng(17)
+    sizes = rng.integers(1, 76490, size=40)
+    index = np.concatenate([[5], 5 + np.cumsum(sizes)]).astype(np.uint64)
+    good = snappy.pack_index(index, 40 * 65536 - 3)
+    accepted = rejected = 0
+    for _ in range(3000):
+        b = bytearray(good[:-4])
+        for _ in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 4))
+            pos = int(rng.integers(8, len(b)))
+            if kind == 0:
+                b[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                b[pos] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 2 and len(b) > 40:
+                del b[pos]
+            else:
+                b.insert(pos, int(rng.integers(0, 256)))
+        blob = bytes(b) + fnv1a(b).to_bytes(4, "little")
+        try:
+            back, ulen, slen = snappy.unpack_index(blob)
+        except snappy.SnappyError:
+            rejected += 1
+            continue
+        accepted += 1
+        assert len(back) == (ulen + 65535) // 65536 + 1 and int(back[-1]) == slen
+        assert np.all(np.diff(back.astype(np.int64)) >= 0) or int(back[-1]) < 2 ** 63
+        assert snappy.unpack_index(snappy.pack_index(back, ulen))[1:] == (ulen, slen)
+    assert rejected > 1000 and accepted + rejected == 3000
