@@ -20,8 +20,15 @@ SNAPPY = "SNAPPY"
 
 # ---- Thrift compact protocol: just enough to read a PageHeader and know where it ends ------------
 class _Reader:
+    """Page headers come out of files: every length is checked against the bytes that are left, nesting is
+    bounded, and read_page_header turns any malformed input into ValueError."""
+    MAX_DEPTH = 16
+
     def __init__(self, buf, pos):
-        self.b, self.p = buf, pos
+        self.b, self.p, self.depth = buf, pos, 0
+
+    def _left(self):
+        return len(self.b) - self.p
 
     def byte(self):
         v = self.b[self.p]
@@ -36,14 +43,16 @@ class _Reader:
             s += 7
             if not c & 0x80:
                 return v
+            if s > 63:
+                raise ValueError("thrift compact: varint too long")
 
     def zigzag(self):
         v = self.varint()
         return (v >> 1) ^ -(v & 1)
 
-    def value(self, t):
-        if t in (1, 2):                      # BOOLEAN_TRUE / BOOLEAN_FALSE (value lives in the type)
-            return t == 1
+    def value(self, t, in_container=False):
+        if t in (1, 2):                      # BOOLEAN_TRUE / BOOLEAN_FALSE (in a struct the value lives in the type)
+            return (self.byte() == 1) if in_container else (t == 1)
         if t == 3:
             return self.byte()
         if t in (4, 5, 6):                   # i16 / i32 / i64
@@ -54,6 +63,8 @@ class _Reader:
             return v
         if t == 8:                           # binary / string
             n = self.varint()
+            if n > self._left():
+                raise ValueError("thrift compact: string runs past the buffer")
             v = bytes(self.b[self.p:self.p + n])
             self.p += n
             return v
@@ -62,22 +73,30 @@ class _Reader:
             n, et = h >> 4, h & 0x0F
             if n == 15:
                 n = self.varint()
-            return [self.value(et) for _ in range(n)]
+            if n > self._left():             # every element takes at least one byte
+                raise ValueError("thrift compact: list runs past the buffer")
+            return [self.value(et, True) for _ in range(n)]
         if t == 11:                          # map
             n = self.varint()
             if n == 0:
                 return {}
+            if 2 * n > self._left():
+                raise ValueError("thrift compact: map runs past the buffer")
             kv = self.byte()
-            return {self.value(kv >> 4): self.value(kv & 0x0F) for _ in range(n)}
+            return {self.value(kv >> 4, True): self.value(kv & 0x0F, True) for _ in range(n)}
         if t == 12:
             return self.struct()
         raise ValueError("thrift compact: unknown type %d" % t)
 
     def struct(self):
+        self.depth += 1
+        if self.depth > self.MAX_DEPTH:
+            raise ValueError("thrift compact: nesting too deep")
         out, fid = {}, 0
         while True:
             h = self.byte()
             if h == 0:
+                self.depth -= 1
                 return out
             delta, t = h >> 4, h & 0x0F
             fid = fid + delta if delta else self.zigzag()
@@ -91,13 +110,19 @@ def read_page_header(buf, pos):
     """PageHeader at buf[pos:]: returns (fields, header_length).  fields: 1 type, 2 uncompressed_page_size,
     3 compressed_page_size, 5 data_page_header, 7 dictionary_page_header, 8 data_page_header_v2."""
     r = _Reader(buf, pos)
-    f = r.struct()
+    try:
+        f = r.struct()
+    except (IndexError, struct.error, TypeError) as e:
+        raise ValueError("malformed page header: %s" % e) from None
+    for need in (1, 2, 3):
+        if not isinstance(f.get(need), int) or f[need] < 0:
+            raise ValueError("malformed page header: field %d" % need)
     return f, r.p - pos
 
 
 def list_pages(file_bytes):
     """All pages of all column chunks of a Parquet file image.  Returns a list of dicts:
-    codec, kind, body (offset of the page body in the file), compressed (bytes of the SNAPPY stream
+    codec, kind, header (offset of the PageHeader), body (offset of the page body in the file), compressed (bytes of the SNAPPY stream
     inside the body), stream (offset of that stream), uncompressed (its decoded length), prefix (bytes
     of the body that are stored uncompressed in front of it: the levels of a v2 data page)."""
     import io
@@ -120,7 +145,7 @@ def list_pages(file_bytes):
                     prefix = h2.get(5, 0) + h2.get(6, 0)       # definition + repetition level bytes
                     compressed = h2.get(7, True)
                 pages.append({"codec": col.compression if compressed else "UNCOMPRESSED", "kind": kind,
-                              "body": body, "prefix": prefix, "stream": body + prefix,
+                              "header": pos, "body": body, "prefix": prefix, "stream": body + prefix,
                               "compressed": csize - prefix, "uncompressed": usize - prefix})
                 pos = body + csize
     return pages

@@ -88,3 +88,34 @@ def test_parquet_page_bodies_are_byte_identical_to_the_writer_under_google_rules
     assert len(ours) > 50
     for body, (p, _) in zip(ours, sel):
         assert body == bytes(f[p["stream"]: p["stream"] + p["compressed"]])
+
+
+def test_page_header_reader_rejects_malformed_input_quickly():
+    """page headers come out of files: mutated headers parse or raise ValueError, never hang or blow the stack"""
+    import time
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("2.0", 4096, rows=5_000)
+    pages = pp.list_pages(f)
+    rng = np.random.default_rng(3)
+    t0 = time.time()
+    ok = bad = 0
+    for p in pages[:12]:
+        hdr = bytearray(f[p["header"]: p["body"]])
+        assert pp.read_page_header(bytes(hdr), 0)[1] == len(hdr)
+        for _ in range(400):
+            b = bytearray(hdr)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            try:
+                fields, hl = pp.read_page_header(bytes(b) + bytes(rng.integers(0, 256, 32, dtype=np.uint8)), 0)
+                assert hl > 0 and fields[3] >= 0
+                ok += 1
+            except ValueError:
+                bad += 1
+    assert ok + bad == 12 * 400 and bad > 100
+    assert time.time() - t0 < 60
+    # adversarial lengths: a list / string / nesting that claims more than the buffer holds
+    for blob in (b"\x19\xfc\xff\xff\xff\xff\x0f", b"\x18\xff\xff\xff\xff\x0f", b"\x1c" * 64, b"\x15" + b"\xff" * 12):
+        with pytest.raises(ValueError):
+            pp.read_page_header(blob, 0)
+
