@@ -1,6 +1,10 @@
 // common.cuh -- shared device helpers for libsnappy_b200 (sm_100a only).
 #pragma once
+#ifdef SB200_CPU_EMU  // tools/cpu_warp: one warp of the compress kernels on the CPU (test infrastructure)
+#include "cuda_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace sb200 {
@@ -26,9 +30,14 @@ enum : int {
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
+#ifdef SB200_CPU_EMU
+extern u8 smem[];  // the CTA's dynamic shared memory; a "shared-space address" is an offset into it
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)(reinterpret_cast<const u8*>(p) - smem); }
+#else
 __device__ __forceinline__ u32 smem_u32(const void* p) {
     return (u32)__cvta_generic_to_shared(p);
 }
+#endif
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------------------
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count) {

@@ -75,6 +75,15 @@ struct Chain {
     __device__ __forceinline__ u32 hash(u32 w) const {
         return kLib ? (((w * kHashMul) >> shift) & hmask) : ((w * kHashMul) >> shift);
     }
+#ifdef SB200_CPU_EMU
+    __device__ __forceinline__ u32 tget(u32 h) const {
+        return kSmemTable ? *reinterpret_cast<const u16*>(smem + Ts + 2u * h) : T[h];
+    }
+    __device__ __forceinline__ void tput(u32 h, u32 pos) const {
+        if (kSmemTable) *reinterpret_cast<u16*>(smem + Ts + 2u * h) = (u16)pos;
+        else T[h] = (u16)pos;
+    }
+#else
     __device__ __forceinline__ u32 tget(u32 h) const {
         if (kSmemTable) {
             u16 v;
@@ -91,6 +100,7 @@ struct Chain {
         if (kSmemTable) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
         else asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; st.global.cg.L2::cache_hint.u16 [%0], %1, pol; }" ::"l"(T + h), "h"((u16)pos) : "memory");
     }
+#endif
 
     // ---- emission ---------------------------------------------------------------------------
     static __device__ __forceinline__ u32 copy_bytes(u32 off, u32 M) {  // size of emit_copy!, :306-329
@@ -125,7 +135,9 @@ struct Chain {
     __device__ __forceinline__ void flush() {
         {   // pull the next few KiB of the fragment into L2 ahead of the ip-side loads (32 x 128 B)
             const u32 ahead = (r_lit >> 16) + kStreamAhead + lane * 128u;  // from this lane's ip
+#ifndef SB200_CPU_EMU
             if (ahead < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + ahead));
+#endif
         }
         const bool mine = lane < nrec;
         const u32 lf = r_lit & 0xffffu, ll = mine ? ((r_lit >> 16) - lf) : 0u;

@@ -60,6 +60,13 @@ struct Win : Chain<kSmemTable, kLib> {
     uint4 pre;   // chunk [pre_at, pre_at + 512) loaded ahead of time (one 16-byte group per lane)
     u32 pre_at;
 
+#ifdef SB200_CPU_EMU
+    static u32 lds32(u32 a) { return *reinterpret_cast<const u32*>(smem + a); }
+    template <int kOff>
+    static u32 lds32o(u32 a) { return *reinterpret_cast<const u32*>(smem + a + kOff); }
+    static void sts128(u32 a, uint4 v) { memcpy(smem + a, &v, 16); }
+    static u32 lds8(u32 a) { return smem[a]; }
+#else
     static __device__ __forceinline__ u32 lds32(u32 a) {
         u32 v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -71,6 +78,7 @@ struct Win : Chain<kSmemTable, kLib> {
         asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(kOff) : "memory");
         return v;
     }
+#endif
     // unaligned 32-bit load at position p (lo <= p, p + 8 <= hi); reads may run into the mirror
     __device__ __forceinline__ u32 ring32u(u32 p) const {
         const u32 a = Rs + ((p & ~3u) & rmask);
@@ -103,6 +111,10 @@ struct Win : Chain<kSmemTable, kLib> {
             const u32 p = hi + lane * 16u;
             const uint4 v = (pre_at == hi) ? pre : load_chunk(p);
             const u32 ro = p & rmask;
+#ifdef SB200_CPU_EMU
+            sts128(Rs + ro, v);
+            if (ro < kRingMirror) sts128(Rs + rmask + 1u + ro, v);
+#else
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + ro), "r"(v.x), "r"(v.y),
                          "r"(v.z), "r"(v.w)
                          : "memory");
@@ -110,6 +122,7 @@ struct Win : Chain<kSmemTable, kLib> {
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(Rs + rmask + 1u + ro), "r"(v.x),
                              "r"(v.y), "r"(v.z), "r"(v.w)
                              : "memory");
+#endif
             hi += kRingChunk;
             if (hi < nstage) {  // the next chunk: issued now, stored when the window gets there
                 pre = load_chunk(hi + lane * 16u);
@@ -128,8 +141,13 @@ struct Win : Chain<kSmemTable, kLib> {
         while (ip + M < n) {
             u32 x, y;
             if (cand + M >= lo && ip + M + 32u <= hi) {
+#ifdef SB200_CPU_EMU
+                x = lds8(Rs + ((cand + M + lane) & rmask));
+                y = lds8(Rs + ((ip + M + lane) & rmask));
+#else
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(x) : "r"(Rs + ((cand + M + lane) & rmask)) : "memory");
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(y) : "r"(Rs + ((ip + M + lane) & rmask)) : "memory");
+#endif
             } else {
                 x = __ldg(F + cand + M + lane);
                 y = __ldg(F + ip + M + lane);
@@ -204,6 +222,15 @@ struct Win : Chain<kSmemTable, kLib> {
                 // far_all: old candidates fetch all 16 bytes at once (one L2 round trip, more wavefronts)
                 // instead of 4 bytes first and the other 12 on a hit
                 const u32 far_all = kFarAll ? 1u : 0u;
+#ifdef SB200_CPU_EMU
+                if (nearp) {
+                    const u32 ra = Rs + (tb & rmask);
+                    c0 = lds32o<0>(ra); c1 = lds32o<4>(ra); c2 = lds32o<8>(ra); c3 = lds32o<12>(ra); c4 = lds32o<16>(ra);
+                } else {
+                    c0 = g[0]; c1 = g[1];
+                    if (far_all) { c2 = g[2]; c3 = g[3]; c4 = g[4]; }
+                }
+#else
                 asm volatile(
                     "{\n"
                     ".reg .pred p;\n"
@@ -223,6 +250,7 @@ struct Win : Chain<kSmemTable, kLib> {
                     : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
                     : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
                     : "memory");
+#endif
                 u32 C0 = __funnelshift_r(c0, c1, tsh);
                 const bool more = V && !nearp && !far_all && C0 == B0;
                 if (__any_sync(kFullMask, more)) {

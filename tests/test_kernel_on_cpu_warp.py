@@ -1,0 +1,67 @@
+"""CPU: the REAL compress kernel source (csrc/compress_window.cuh + compress_chain.cuh, every instantiation of
+k_compress_window) compiled with -DSB200_CPU_EMU and executed as one 32-lane warp of coroutines
+(tools/cpu_warp/cuda_shim.h), fragment by fragment against the oracle.  Unlike tools/emulate_window.c this is not a
+model of the algorithm: it is the kernel's own code (the few inline-PTX statements have C++ twins; the CUDA build's
+SASS is unchanged by them), so lane logic, masks, ring addressing, table commits and emission are checked where no GPU
+exists.  Timing, occupancy and inter-lane memory ordering are what only the GPU tests see."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT
+
+FILES = ["html", "alice29.txt", "fireworks.jpeg", "geo.protodata", "smallrandom1.bin", "sample-tweet.json"]
+
+
+@pytest.fixture(scope="module")
+def warp(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cpu_warp")
+    exe = str(d / "run_window_kernel")
+    obj = str(d / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_window_kernel.cpp"), obj])
+    return exe
+
+
+def run(exe, files, table, rules, ring, kernel="window"):
+    env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel)
+    p = subprocess.run([exe] + files, env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = [l for l in p.stdout.splitlines() if "fragments" in l]
+    assert len(lines) == len(files)
+    for l in lines:
+        assert " 0 mismatches" in l, l
+
+
+@pytest.mark.parametrize("table,ring", [("smem", 2048), ("global", 1024)])
+@pytest.mark.parametrize("rules", [0, 1, 2])
+def test_kernel_source_matches_oracle_on_fixtures(warp, table, ring, rules):
+    run(warp, [os.path.join(DATA, f) for f in FILES], table, rules, ring)
+
+
+def test_kernel_source_on_boundary_sizes_and_patterns(warp, tmp_path):
+    rng = np.random.default_rng(77)
+    words = [rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8).tobytes() for _ in range(200)]
+    text = b" ".join(words[i] for i in rng.integers(0, 200, 40000))
+    blobs = [text[:n] for n in (1, 14, 15, 16, 17, 31, 32, 33, 60, 61, 76, 77, 255, 4096, 65535, 65536, 65537,
+                                65536 + 15, 65536 + 16, 2 * 65536)]
+    blobs += [bytes(range(60)), b"a" * 70 + bytes(range(100, 130)), b"ab" * 3000 + bytes(range(256)) * 3,
+              b"\0" * 70000, bytes(rng.integers(0, 4, 70000, dtype=np.uint8)),
+              (b"0123456789abcdef" * 5 + b"X") * 900]
+    files = []
+    for i, b in enumerate(blobs):
+        p = tmp_path / ("b%02d.bin" % i)
+        p.write_bytes(b)
+        files.append(str(p))
+    for table, ring in (("smem", 2048), ("global", 1024)):
+        for rules in (0, 2):
+            run(warp, files, table, rules, ring)
+
+
+@pytest.mark.parametrize("table", ["smem", "global"])
+def test_step_wise_chain_kernel_source_matches_oracle(warp, table):
+    """k_compress_chain (option window=0; also the slow paths of the window kernel)"""
+    run(warp, [os.path.join(DATA, f) for f in FILES], table, 0, 2048, kernel="chain")
