@@ -65,3 +65,61 @@ def test_kernel_source_on_boundary_sizes_and_patterns(warp, tmp_path):
 def test_step_wise_chain_kernel_source_matches_oracle(warp, table):
     """k_compress_chain (option window=0; also the slow paths of the window kernel)"""
     run(warp, [os.path.join(DATA, f) for f in FILES], table, 0, 2048, kernel="chain")
+
+
+# ---------------------------------------------------------------------------------------------- the decoder
+@pytest.fixture(scope="module")
+def decode_warp(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cpu_warp_decode")
+    exe = str(d / "run_decode_kernel")
+    obj = str(d / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_decode_kernel.cpp"), obj])
+    return exe
+
+
+def run_decode(exe, mode, files):
+    p = subprocess.run([exe, mode] + files, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert len(lines) == len(files)
+    for l in lines:
+        assert "0 mismatches" in l or "header rejected" in l, l
+    return lines
+
+
+def test_indexed_decoder_source_round_trips(decode_warp, tmp_path):
+    """k_decode_fragments (the fused window-parallel decoder) on oracle-compressed fixtures and patterns:
+    overlapping copies (runs, short periods), long literals, 64-byte copy splitting"""
+    rng = np.random.default_rng(5)
+    blobs = [b"\0" * 70000, b"ab" * 40000, (b"0123456789abcdef" * 5 + b"X") * 900, bytes(range(256)) * 300,
+             bytes(rng.integers(0, 4, 70000, dtype=np.uint8)), bytes(rng.integers(0, 256, 66000, dtype=np.uint8)),
+             b"x", b"a" * 70 + bytes(range(100, 130))]
+    files = [os.path.join(DATA, f) for f in FILES + ["urls.10K", "kppkn.gtb"]]
+    for i, b in enumerate(blobs):
+        p = tmp_path / ("d%02d.bin" % i)
+        p.write_bytes(b)
+        files.append(str(p))
+    run_decode(decode_warp, "indexed", files)
+
+
+def test_exact_decoder_source_matches_oracle_statuses(decode_warp, oracle, tmp_path):
+    """k_decode_serial: the reference's decoder semantics (src/internal.jl:411-527) -- foreign streams, the
+    reference's must-throw streams (test/runtests.jl:62-123) with status AND failing output position, and streams the
+    oracle made"""
+    from conftest import corrupt_streams, read_data
+    files = [os.path.join(DATA, f) for f in ("alice29.snappy", "baddata1.snappy", "baddata2.snappy", "baddata3.snappy")]
+    for name, data in corrupt_streams(oracle):
+        p = tmp_path / (name + ".snappy")
+        p.write_bytes(data)
+        files.append(str(p))
+    for name in ("html", "sample-tweet.json", "fireworks.jpeg"):
+        p = tmp_path / (name + ".oracle.snappy")
+        p.write_bytes(oracle.compress(read_data(name)))
+        files.append(str(p))
+        q = tmp_path / (name + ".truncated.snappy")
+        q.write_bytes(oracle.compress(read_data(name))[:-7])
+        files.append(str(q))
+    lines = run_decode(decode_warp, "exact", files)
+    assert any("status 3 (oracle 3), produced 19791" in l for l in lines)   # SURVEY.md 8(c): baddata1

@@ -44,6 +44,7 @@ struct Warp {
     char* stacks[kLanes];
     bool done[kLanes];
     int cur = 0;
+    uint32_t tid_base = 0, block = 0, block_dim = 32;  // which warp of which CTA this is
     // collective state
     uint32_t vals[kLanes], snap[kLanes];
     int arrived = 0;
@@ -126,13 +127,15 @@ inline void run_warp(void (*entry)(void*), void* arg) {
 struct Idx {
     uint32_t x, y, z;
 };
-inline Idx thread_idx() { return Idx{(uint32_t)W().cur, 0, 0}; }
+inline Idx thread_idx() { return Idx{W().tid_base + (uint32_t)W().cur, 0, 0}; }
+inline Idx block_idx() { return Idx{W().block, 0, 0}; }
+inline Idx block_dim() { return Idx{W().block_dim, 1, 1}; }
 
 }  // namespace cpu_warp
 
 #define threadIdx (cpu_warp::thread_idx())
-#define blockIdx (cpu_warp::Idx{0, 0, 0})
-#define blockDim (cpu_warp::Idx{32, 1, 1})
+#define blockIdx (cpu_warp::block_idx())
+#define blockDim (cpu_warp::block_dim())
 
 // ---- warp collectives (full mask only: the kernels never use another) -----------------------------------------
 static inline void check_full(uint32_t mask) {
@@ -162,6 +165,13 @@ static inline uint32_t __ballot_sync(uint32_t mask, int pred) {
     return r;
 }
 static inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline uint32_t __reduce_or_sync(uint32_t mask, uint32_t v) {
+    check_full(mask);
+    uint32_t all[32], r = 0;
+    cpu_warp::exchange(v, all);
+    for (int l = 0; l < 32; l++) r |= all[l];
+    return r;
+}
 static inline uint32_t __match_any_sync(uint32_t mask, uint32_t v) {
     check_full(mask);
     uint32_t all[32], r = 0;
@@ -193,3 +203,12 @@ static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
     *p = old + v;
     return old;
 }
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
+    const uint32_t old = *p;
+    *p = old | v;
+    return old;
+}
+template <typename T>
+static inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T>
+static inline T max(T a, T b) { return a > b ? a : b; }
