@@ -123,3 +123,46 @@ def test_exact_decoder_source_matches_oracle_statuses(decode_warp, oracle, tmp_p
         files.append(str(q))
     lines = run_decode(decode_warp, "exact", files)
     assert any("status 3 (oracle 3), produced 19791" in l for l in lines)   # baddata1
+
+
+# ---------------------------------------------------------------------------------------------- the index-free parse
+def test_parse_kernel_sources_build_the_true_index(oracle, tmp_path):
+    """parse.cuh passes A-E (one thread per 1 KiB of compressed bytes), launched as build_index_segment does, whole
+    stream and cut into two segments: whenever the parse accepts a stream its index equals a sequential walk's, clean
+    streams (Snappy.jl's, libsnappy's, current Google snappy's) are accepted, foreign / corrupt ones declined"""
+    pa = pytest.importorskip("pyarrow")
+    from conftest import corrupt_streams, read_data
+    d = tmp_path
+    exe = str(d / "run_parse_kernel")
+    obj = str(d / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_parse_kernel.cpp"), obj])
+    rng = np.random.default_rng(9)
+    raws = {n: read_data(n) for n in ("html", "alice29.txt", "fireworks.jpeg", "urls.10K", "sample-tweet.json", "kppkn.gtb")}
+    raws["zeros"] = b"\0" * 300000
+    raws["period"] = (b"0123456789abcdef" * 5 + b"X") * 4000
+    raws["random"] = bytes(rng.integers(0, 256, 200000, dtype=np.uint8))      # 64 KiB literals: chunks inside literals
+    raws["mixed"] = raws["random"][:70000] + raws["html"][:50000] + raws["random"][70000:140001] + raws["zeros"][:65536]
+    files, clean = [], []
+    for name, raw in raws.items():
+        for tag, comp in (("jl", oracle.compress(raw)), ("v1", oracle.compress_rules(raw, 1)),
+                          ("google", pa.Codec("snappy").compress(raw, asbytes=True))):
+            p = d / ("%s.%s.snappy" % (name, tag))
+            p.write_bytes(comp)
+            files.append(str(p))
+            clean.append(str(p))
+    for name, data in corrupt_streams(oracle):
+        p = d / ("bad_%s.snappy" % name)
+        p.write_bytes(data)
+        files.append(str(p))
+    files += [os.path.join(DATA, f) for f in ("alice29.snappy", "baddata1.snappy", "baddata2.snappy", "baddata3.snappy")]
+    p = subprocess.run([exe] + files, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert len(lines) == len(files)
+    for f, l in zip(files, lines):
+        assert "0 mismatches" in l or "no body to parse" in l, l
+        if f in clean:
+            assert "stream valid/clean, parse accepted" in l, l
+    assert any("alice29.snappy" in l and "not clean, parse declined" in l for l in lines)

@@ -44,7 +44,7 @@ struct Warp {
     char* stacks[kLanes];
     bool done[kLanes];
     int cur = 0;
-    uint32_t tid_base = 0, block = 0, block_dim = 32;  // which warp of which CTA this is
+    uint32_t tid_base = 0, block = 0, block_dim = 32, grid_dim = 1;  // which warp of which CTA this is
     // collective state
     uint32_t vals[kLanes], snap[kLanes];
     int arrived = 0;
@@ -130,12 +130,32 @@ struct Idx {
 inline Idx thread_idx() { return Idx{W().tid_base + (uint32_t)W().cur, 0, 0}; }
 inline Idx block_idx() { return Idx{W().block, 0, 0}; }
 inline Idx block_dim() { return Idx{W().block_dim, 1, 1}; }
+inline Idx grid_dim() { return Idx{W().grid_dim, 1, 1}; }
+
+// kernels whose threads never meet at a collective (one thread per item): every thread of every CTA, one after the other
+template <typename K, typename... A>
+inline void launch_independent_threads(uint32_t grid, uint32_t block, K kernel, A... args) {
+    Warp& w = W();
+    w.block_dim = block;
+    w.grid_dim = grid;
+    w.cur = 0;
+    for (uint32_t b = 0; b < grid; b++)
+        for (uint32_t t = 0; t < block; t++) {
+            w.block = b;
+            w.tid_base = t;
+            kernel(args...);
+        }
+    w.block = w.tid_base = 0;
+    w.block_dim = 32;
+    w.grid_dim = 1;
+}
 
 }  // namespace cpu_warp
 
 #define threadIdx (cpu_warp::thread_idx())
 #define blockIdx (cpu_warp::block_idx())
 #define blockDim (cpu_warp::block_dim())
+#define gridDim (cpu_warp::grid_dim())
 
 // ---- warp collectives (full mask only: the kernels never use another) -----------------------------------------
 static inline void check_full(uint32_t mask) {
@@ -201,6 +221,19 @@ static inline void __threadfence() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
     const uint32_t old = *p;
     *p = old + v;
+    return old;
+}
+static inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
+    check_full(mask);
+    uint32_t all[32], r = 0;
+    cpu_warp::exchange(v, all);
+    for (int l = 0; l < 32; l++) r = all[l] > r ? all[l] : r;
+    return r;
+}
+static inline void __threadfence_system() {}
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+    const uint32_t old = *p;
+    if (v > old) *p = v;
     return old;
 }
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
