@@ -108,6 +108,14 @@ __device__ __forceinline__ u32 warp_match_length(const u8* F, u32 a, u32 b, u32 
 // returns the updated count.
 __device__ __forceinline__ u32 load_fragment(u8* F, u64* bar, const u8* g, u32 n, u32 lane,
                                              u32 phase) {
+#ifdef SB200_CPU_EMU  // tools/cpu_warp: no TMA, no mbarrier -- the lanes copy
+    (void)bar;
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) F[i] = g[i];
+    if (lane < kFragPad) F[n + lane] = 0;
+    __syncwarp();
+    return phase;
+#else
     u32 body = 0;
     if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) body = n & ~15u;
     if (phase == 0) {
@@ -132,6 +140,7 @@ __device__ __forceinline__ u32 load_fragment(u8* F, u64* bar, const u8* g, u32 n
     }
     __syncwarp();
     return phase;
+#endif
 }
 
 // Zero the hash table (position per hash, 0 == empty; the reference stores pos-1 with

@@ -166,3 +166,22 @@ def test_parse_kernel_sources_build_the_true_index(oracle, tmp_path):
         if f in clean:
             assert "stream valid/clean, parse accepted" in l, l
     assert any("alice29.snappy" in l and "not clean, parse declined" in l for l in lines)
+
+
+# ---------------------------------------------------------------------------------------------- batched pages
+@pytest.mark.parametrize("rules", [0, 2])
+def test_page_kernel_sources_match_oracle_and_round_trip(tmp_path, rules):
+    """k_compress_pages / k_decode_pages (one warp per independent stream, BASELINE config 4): 4 KiB pages, ragged and
+    empty pages, one multi-fragment page; compressed bytes == the oracle's stream per page, decode gives the page back"""
+    exe = str(tmp_path / "run_pages_kernel")
+    obj = str(tmp_path / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_pages_kernel.cpp"), obj])
+    files = [os.path.join(DATA, f) for f in ("html", "alice29.txt", "fireworks.jpeg", "sample-tweet.json", "geo.protodata")]
+    p = subprocess.run([exe] + files, env=dict(os.environ, RULES=str(rules)), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert len(lines) == len(files)
+    for l in lines:
+        assert "0 mismatches" in l, l

@@ -216,6 +216,12 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
+template <typename T>
+static inline T __ldcg(const T* p) { return *p; }
+static inline void __syncthreads() {  // kernels with several cooperating warps per CTA are not modelled
+    fprintf(stderr, "cpu_warp: __syncthreads() reached: this kernel needs more than one warp\n");
+    abort();
+}
 static inline void __nanosleep(unsigned) { cpu_warp::yield_lane(); }
 static inline void __threadfence() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
