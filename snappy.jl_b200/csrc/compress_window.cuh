@@ -47,7 +47,10 @@ constexpr bool kFarAll = SB200_FAR_ALL != 0;
 #define SB200_M_BRANCHFREE 1
 #endif
 
-template <bool kSmemTable, bool kLib = false>
+// kSlowCont (option `slowcont`, experimental, off): a copy of >= 16 bytes is extended inside the hop loop and the
+// chain goes on in the same window when it lands there, instead of ending the round (tools/emulate_window.c
+// SLOWCONT=1: 1-8 % fewer rounds).  Exact (tools/cpu_warp); not yet measured on the GPU.
+template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
 struct Win : Chain<kSmemTable, kLib> {
     using Base = Chain<kSmemTable, kLib>;
     using Base::F;
@@ -344,6 +347,24 @@ struct Win : Chain<kSmemTable, kLib> {
                 // ------------- follow the chain through the window (warp-uniform)
                 for (;;) {
                     if (d & (1u << 13)) scan_s = a + cur + 1u;  // :162 a new scan started behind lane cur
+                    if (kSlowCont && (d & 7u) == K_SLOW) {
+                        const u32 e = (d >> 3) & 31u, ip = a + e, cand = d >> 16;
+                        const u32 M = extend(ip, cand, 16);
+                        this->keep(lit_from, ip, cand, M);  // :200,:217
+                        lit_from = ip + M;
+                        if ((int)lit_from >= lim) {  // :222
+                            d = K_FIN;
+                            break;
+                        }
+                        if (e + M >= 32u) {
+                            d = K_NEXTARR | (1u << 14);
+                            break;
+                        }
+                        cur = e + M;
+                        d = __shfl_sync(kFullMask, desc, cur);
+                        insacc |= __shfl_sync(kFullMask, ins, cur);
+                        continue;
+                    }
                     if ((d & 7u) != K_COPY) break;
                     const u32 e = (d >> 3) & 31u, me = (d >> 8) & 31u;
                     this->keep(lit_from, a + e, d >> 16, me);  // :200,:217
@@ -396,7 +417,7 @@ struct Win : Chain<kSmemTable, kLib> {
 // (behind the tables for the shared-table variant).
 // kLib (option `rules`): libsnappy's rules; lib_rules = 1: libsnappy <= 1.1.7 (hash >> shift, <= 16384 buckets),
 // 2: Google snappy >= 1.1.9 ((hash >> 17) & mask, <= 32768 buckets: 64 KiB tables); table size per fragment.
-template <bool kSmemTable, bool kLib = false>
+template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
 __global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
 k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
                   const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
@@ -450,7 +471,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        Win<kSmemTable, kLib> ch;
+        Win<kSmemTable, kLib, kSlowCont> ch;
         ch.hmask = entries - 1u;
         ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;

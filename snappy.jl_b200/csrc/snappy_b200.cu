@@ -60,6 +60,7 @@ struct Options {
     int l2_persist = 0;         // 1 = pin the global hash tables in L2 (access policy window on the side stream)
     int rules = 0;              // emission rules: 0 = Snappy.jl (the reference, default), 1 = libsnappy <= 1.1.7,
                                 // 2 = Google snappy >= 1.1.9 (byte-identical to pyarrow's bundled codec)
+    int slowcont = 0;           // 1 = window kernel variant that extends long copies inside the hop loop (experimental)
     int window = 1;             // 1 = window-parallel kernel (compress_window.cuh), 0 = step-wise chain kernel
     int ring_smem = 2048;       // history ring per shared-table warp (bytes, power of two >= 1024)
     int ring_l2 = 1024;         // history ring per global-table warp
@@ -142,6 +143,7 @@ void apply_option(const char* name, int value) {
         cudaMemcpyToSymbol(g_dbg_skip_emit, &v, 4);
     }
     else if (!strcmp(name, "rules")) g_ctx.opt.rules = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (!strcmp(name, "slowcont")) g_ctx.opt.slowcont = value != 0;
     else if (!strcmp(name, "window")) g_ctx.opt.window = value;
     else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
     else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
@@ -211,6 +213,12 @@ int ctx_init_locked(int device) {
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -376,6 +384,10 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             k_compress_window<true, true><<<ctas_a, wa * 32, (size_t)wa * (tab_bytes + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
                 ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules);
+        else if (window && c.opt.slowcont)
+            k_compress_window<true, false, true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
         else if (window)
             k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
@@ -407,6 +419,11 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
                 gate ? gate->div : 1u, rules);
+        else if (window && c.opt.slowcont)
+            k_compress_window<false, false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
+                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
+                gate ? gate->div : 1u);
         else if (window)
             k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,

@@ -26,8 +26,8 @@ def warp(tmp_path_factory):
     return exe
 
 
-def run(exe, files, table, rules, ring, kernel="window"):
-    env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel)
+def run(exe, files, table, rules, ring, kernel="window", slowcont=0):
+    env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel, SLOWCONT=str(slowcont))
     p = subprocess.run([exe] + files, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     lines = [l for l in p.stdout.splitlines() if "fragments" in l]
@@ -65,6 +65,13 @@ def test_kernel_source_on_boundary_sizes_and_patterns(warp, tmp_path):
 def test_step_wise_chain_kernel_source_matches_oracle(warp, table):
     """k_compress_chain (option window=0; also the slow paths of the window kernel)"""
     run(warp, [os.path.join(DATA, f) for f in FILES], table, 0, 2048, kernel="chain")
+
+
+@pytest.mark.parametrize("table,ring", [("smem", 2048), ("global", 1024)])
+def test_slowcont_variant_source_matches_oracle(warp, table, ring):
+    """option `slowcont` (experimental, off by default, not yet measured on a GPU): long copies are extended inside
+    the hop loop and the chain goes on in the same window"""
+    run(warp, [os.path.join(DATA, f) for f in FILES + ["urls.10K"]], table, 0, ring, slowcont=1)
 
 
 # ---------------------------------------------------------------------------------------------- the decoder

@@ -4,7 +4,7 @@
 // source itself -- not a model of it -- makes the reference's decisions (tests/test_kernel_on_cpu_warp.py).
 //
 //   g++ -O1 -std=c++17 -DSB200_CPU_EMU -Itools/cpu_warp tools/cpu_warp/run_window_kernel.cpp oracle/snappy_oracle.c
-//   TABLE=smem|global RULES=0|1|2 RING=2048 KERNEL=window|chain ./a.out file...
+//   TABLE=smem|global RULES=0|1|2 RING=2048 KERNEL=window|chain SLOWCONT=0|1 ./a.out file...
 #include "../../snappy.jl_b200/csrc/compress_window.cuh"
 
 extern "C" {
@@ -28,6 +28,7 @@ struct Args {
     u16* gtables;
     u32 ring, rules;
     bool chain;  // KERNEL=chain: the step-wise kernel (option window=0), rules 0 only
+    bool slowcont;  // SLOWCONT=1: the experimental window variant (option slowcont), rules 0 only
 };
 
 template <bool kSmem, bool kLib>
@@ -40,6 +41,15 @@ static void entry(void* p) {
     if (a.chain) {
         if (a.smem_table) k_compress_chain<true>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables, 32u, 0u, nullptr, 0u);
         else k_compress_chain<false>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables, 16u, 0u, nullptr, 0u);
+        return;
+    }
+    if (a.slowcont) {
+        if (a.smem_table)
+            k_compress_window<true, false, true>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables,
+                                                  0u, nullptr, 0u, a.ring, nullptr, nullptr, 1u, 0u);
+        else
+            k_compress_window<false, false, true>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables,
+                                                   0u, nullptr, 0u, a.ring, nullptr, nullptr, 1u, 0u);
         return;
     }
     if (a.smem_table) {
@@ -57,7 +67,8 @@ int main(int argc, char** argv) {
     const u32 rules = getenv("RULES") ? (u32)atoi(getenv("RULES")) : 0u;
     const u32 ring = getenv("RING") ? (u32)atoi(getenv("RING")) : 2048u;
     const bool chain = getenv("KERNEL") && !strcmp(getenv("KERNEL"), "chain");
-    if (chain && rules) {
+    const bool slowcont = getenv("SLOWCONT") && atoi(getenv("SLOWCONT")) != 0;
+    if ((chain || slowcont) && rules) {
         fprintf(stderr, "KERNEL=chain has no rules instantiation\n");
         return 2;
     }
@@ -92,7 +103,7 @@ int main(int argc, char** argv) {
         u32 counter = 0;
         u32 entries = sjo_hashtable_entries((u64)sz), shift = 32;
         for (u32 e = entries; e > 1; e >>= 1) shift--;
-        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain};
+        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont};
         cpu_warp::W().collectives = 0;
         cpu_warp::run_warp(entry, &a);
         // the oracle, fragment by fragment
@@ -116,7 +127,7 @@ int main(int argc, char** argv) {
             }
         }
         printf("%s: %u fragments, %ld mismatches (%s kernel, %s table, rules %u, ring %u, %llu collectives)\n", argv[ai], nfrag, bad,
-               chain ? "chain" : "window", smem_table ? "shared" : "global", rules, ring, (unsigned long long)cpu_warp::W().collectives);
+               chain ? "chain" : (slowcont ? "window+slowcont" : "window"), smem_table ? "shared" : "global", rules, ring, (unsigned long long)cpu_warp::W().collectives);
         failed += bad != 0;
         free(in); free(tail); free(scratch); free(sizes); free(gtables); free(want); free(table);
     }
