@@ -303,13 +303,14 @@ def test_batched_shard_api(dev, oracle):
     {"window": 1, "smem_chains": 0},     # window kernel, global tables only
     {"window": 1, "wide": 4},            # 4 warps per fragment (compress_wide.cuh)
     {"window": 1, "wide": 2},
+    {"window": 1, "slowcont": 1},        # long copies extended inside the hop loop (measured slower: off by default)
 ])
 def test_compress_kernel_variants_bit_exact(dev, oracle, options):
     """every compress kernel in the library produces the oracle's bytes (the default is the window
     kernel with both table placements running side by side)"""
     import torch
     from snappy_jl_b200 import synth
-    defaults = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6}
+    defaults = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6, "slowcont": 0}
     raw = np.concatenate([synth.mix(96, seed=5, tail=777),
                           np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
                                         dtype=np.uint8)])
