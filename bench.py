@@ -56,6 +56,7 @@ def measured_peak():
 def gpu_local_cpus(dev_index):
     """CPUs on the NUMA node the GPU's PCIe root hangs off (sysfs), or None."""
     try:
+        import torch
         pr = torch.cuda.get_device_properties(dev_index)
         bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
