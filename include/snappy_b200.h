@@ -180,6 +180,9 @@ int snappy_b200_last_launch_count(int which);
  *                to the C++ library current consumers link (checked against pyarrow's bundled codec).
  * Every setting produces a valid Snappy stream that any decoder (this one, Snappy.jl, libsnappy) accepts. */
 void snappy_b200_set_option(const char *name, int value);
+/* Current value of an option, or -1 for a name this build does not know.  "experiments" reads 1 in a build that
+ * also holds the measured-and-rejected kernel designs (make -C snappy.jl_b200/csrc exp), 0 in the product build. */
+int snappy_b200_get_option(const char *name);
 
 #ifdef __cplusplus
 }

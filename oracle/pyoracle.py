@@ -69,6 +69,8 @@ def lib():
         L.sjo_compress_rules.argtypes = [u8p, ctypes.c_size_t, u8p, szp, ctypes.c_int]
         L.sjo_uncompressed_length.restype = ctypes.c_int
         L.sjo_uncompressed_length.argtypes = [u8p, ctypes.c_size_t, szp]
+        L.sjo_char_table_entry.restype = ctypes.c_uint16
+        L.sjo_char_table_entry.argtypes = [ctypes.c_uint32]
         L.sjo_uncompress_ex.restype = ctypes.c_int
         L.sjo_uncompress_ex.argtypes = [u8p, ctypes.c_size_t, u8p, szp, szp]
         _lib = L
@@ -181,3 +183,8 @@ def find_match_length(a, i1, i2, limit):
     """0-based, `limit` exclusive."""
     arr = _as_u8(a)
     return lib().sjo_find_match_length(_ptr(arr), i1, i2, limit)
+
+
+def char_table():
+    """CHAR_TABLE (internal.jl:47-80) as the C oracle regenerates it: 256 ints."""
+    return [int(lib().sjo_char_table_entry(c)) for c in range(256)]

@@ -351,7 +351,7 @@ int sjo_uncompressed_length(const uint8_t *in, size_t n, size_t *result) {
 }
 
 /* internal.jl:47-80 regenerated from the format definition instead of the literal table */
-static uint16_t char_table_entry(uint32_t c) {
+uint16_t sjo_char_table_entry(uint32_t c) {
     uint32_t kind = c & 3, hi = c >> 2;
     if (kind == 0) return (uint16_t)(hi < 60 ? (hi + 1) : (1 | ((hi - 59) << 11)));
     if (kind == 1) return (uint16_t)((4 + (hi & 7)) | ((c >> 5) << 8) | (1u << 11));
@@ -374,7 +374,7 @@ int sjo_uncompress_ex(const uint8_t *in, size_t L, uint8_t *out, size_t *out_len
         uint32_t c = in[ip++];
         uint32_t tag = 0;                                  /* :426-430 zero-padded 4-byte trailer */
         for (int k = 0; k < 4 && ip + (size_t)k < L; k++) tag |= (uint32_t)in[ip + k] << (8 * k);
-        uint32_t entry = char_table_entry(c);              /* :435 */
+        uint32_t entry = sjo_char_table_entry(c);          /* :435 */
         uint32_t len = entry & 0xff, taglen = entry >> 11;
         uint32_t trailer = tag & wordmask[taglen];         /* :438 */
         ip += taglen;                                      /* may run past L; see avail_in below */

@@ -58,6 +58,8 @@ int sjo_compress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
 size_t sjo_compress_fragment_rules(const uint8_t *frag, size_t n, uint8_t *out, uint16_t *table,
                                    uint32_t entries, int rules);
 int sjo_compress_rules(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len, int rules);
+/* CHAR_TABLE[c] (internal.jl:47-80) as this oracle regenerates it; tests hold it to the reference's literal table */
+uint16_t sjo_char_table_entry(uint32_t c);
 int sjo_uncompressed_length(const uint8_t *in, size_t n, size_t *result);
 int sjo_uncompress(const uint8_t *in, size_t n, uint8_t *out, size_t *out_len);
 /* same as sjo_uncompress, additionally reports the output position at which the error fired */

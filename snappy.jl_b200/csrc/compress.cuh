@@ -214,8 +214,9 @@ __device__ __forceinline__ void compress_fragment_serial(const u8* F, u16* T, co
     if (next_emit < n) em.literal(F, next_emit, n - next_emit);  // :242-248
 }
 
+#ifdef SB200_EXPERIMENTS  // the first two designs (74 ms and 115 ms per GiB): kept bit-exact-tested, not shipped
 // =============================================================================================
-// K1 (default): warp-specialised, lane-speculative fragment compressor.
+// K1 v2 (experiment): warp-specialised, lane-speculative fragment compressor.
 //
 // CTA = 2 warps per fragment.  Warp 0 ("decider") walks the reference's serial decision chain
 // (src/internal.jl:162-239) but evaluates up to 32 table probes per round in its lanes:
@@ -620,6 +621,8 @@ k_compress_fragments_serial(const u8* __restrict__ g_in, u64 shard_len, u32 shif
     compress_fragment_serial(F, T, n, shift, em);
     if (lane == 0) frag_sizes[frag] = em.op;
 }
+
+#endif  // SB200_EXPERIMENTS
 
 // K1b: batched pages -- one CTA (one warp) per independent stream (src/Snappy.jl:20-36 per page:
 // own varint header, table sized from the page length).  Fragments of a page are compressed one

@@ -42,7 +42,9 @@ __device__ __forceinline__ u32 ldg32u(const u8* p) {
 // probe offsets of the skip heuristic (skip starts at 32, step = skip >> 5, :162-172); filled once
 // by k_init_probe_offsets.  Only scan rounds past the first 32 probes read it (incompressible data).
 __device__ u32 g_probe_offsets[kChainPoEntries];
+#ifdef SB200_EXPERIMENTS
 __device__ u32 g_dbg_skip_emit = 0;  // upper-bound experiments: what would free emission buy
+#endif
 
 __global__ void k_init_probe_offsets() {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -153,10 +155,12 @@ struct Chain {
         }
         const u32 pos = op + incl - sz;
         op += __shfl_sync(kFullMask, incl, 31);
+#ifdef SB200_EXPERIMENTS
         if (g_dbg_skip_emit) {  // measurement only (option dbg_skip_emit): sizes stay right, bytes are not written
             nrec = 0;
             return;
         }
+#endif
         if (ll) {
             const u32 nm1 = ll - 1;
             if (ll < kLitShort) {
@@ -376,6 +380,7 @@ struct ShardDesc {
     u32 frag_begin, nfrag, shift, pad_;
 };
 
+#ifdef SB200_EXPERIMENTS  // the step-wise kernel (option window=0, 20.9 ms per GiB); its Chain struct above is the slow path of K1w
 // Persistent warps; fragments are pulled from *counter.  One CTA per SM with `blockDim.x / 32` warps:
 // 7 shared-memory tables of 32 KiB fit one CTA (7 x 32 KiB + the 1 KiB the system reserves per CTA
 // <= 227 KiB) where seven 1-warp CTAs would not.  Warps never synchronise with each other.
@@ -438,5 +443,7 @@ k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shif
         __syncwarp();
     }
 }
+
+#endif  // SB200_EXPERIMENTS
 
 }  // namespace sb200

@@ -416,6 +416,7 @@ struct Win : Chain<kSmemTable, kLib> {
 
 // Persistent warps, as k_compress_chain; each warp additionally owns `ring_bytes` of shared memory
 // (behind the tables for the shared-table variant).
+// order (optional): the k-th fragment pulled is order[k] (schedule.cuh); the bytes do not depend on it.
 // kLib (option `rules`): libsnappy's rules; lib_rules = 1: libsnappy <= 1.1.7 (hash >> shift, <= 16384 buckets),
 // 2: Google snappy >= 1.1.9 ((hash >> 17) & mask, <= 32768 buckets: 64 KiB tables); table size per fragment.
 template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
@@ -424,7 +425,8 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
                   const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
                   u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
                   const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes,
-                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1, u32 lib_rules = 0) {
+                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1, u32 lib_rules = 0,
+                  const u32* __restrict__ order = nullptr) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarp = blockDim.x >> 5;
@@ -439,6 +441,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         if (lane == 0) frag = atomicAdd(counter, 1u);
         frag = __shfl_sync(kFullMask, frag, 0);
         if (frag >= nfrag) break;
+        if (order) frag = order[frag];  // schedule.cuh: expensive fragments first (never together with `ready`)
         if (ready) {  // streamed input (host-buffer API): wait until this fragment and the one behind it
                       // (the kernel reads a few bytes past a fragment's end) have landed
             if (lane == 0) {

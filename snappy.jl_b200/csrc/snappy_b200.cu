@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,9 +19,12 @@
 #include "compress.cuh"
 #include "compress_chain.cuh"
 #include "compress_window.cuh"
+#ifdef SB200_EXPERIMENTS
 #include "compress_wide.cuh"
+#endif
 #include "decompress.cuh"
 #include "parse.cuh"
+#include "schedule.cuh"
 
 using namespace sb200;
 
@@ -50,6 +54,8 @@ struct DevBuf {
 };
 
 constexpr int kMaxPipeChunks = 72;                 // 4 GiB / 64 MiB, plus slack
+constexpr size_t kPinnedBytes = 64 * 1024;         // small pinned readback area of a lane
+constexpr size_t kPinnedShardLens = 8192;          // offset of the per-shard lengths of the batched shard API (<= 4096 x u64)
 constexpr size_t kPipeChunkFragsDefault = 4096;    // fragments per pipeline chunk (256 MiB)
 
 struct Options {
@@ -77,16 +83,22 @@ struct Options {
     int uncompress_segments = 8;  // streamed host-buffer uncompress: segments the stream is parsed in (2, 4 or 8)
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
+    int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
+    int pin_host = 1;           // host-buffer API on pageable memory: register the caller's buffers for the call
 };
+
+Options g_opt;             // process-wide (snappy_b200_set_option / SNAPPY_B200_OPTIONS)
+std::mutex g_opt_mu;
 
 struct Context {
     std::mutex mu;
     bool ready = false;
     int device = -1;
+    int lane = 0;
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
     // scratch for compress
-    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags;
+    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags, order;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr, s_pack = nullptr;  // host-buffer API pipeline
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
@@ -95,16 +107,33 @@ struct Context {
     DevBuf result, parse_a, parse_b, parse_c, index;
     // staging for the host-buffer API
     DevBuf stage_in, stage_out;
-    void* pinned = nullptr;  // small pinned readback area (4 KiB)
+    void* pinned = nullptr;  // small pinned readback area (kPinnedBytes)
     void* pinned_zero = nullptr;  // kTailPad zero bytes (pinned): pads go up through the copy engine
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[2] = {0.f, 0.f};
     int last_launches[2] = {0, 0};
     bool ev_pending[2] = {false, false};
-    Options opt;
+    Options& opt = g_opt;
 };
 
-Context g_ctx;
+// One Context (scratch buffers, streams, events) per device and LANE.  A call takes a free lane of the device it
+// addresses, so that concurrent host threads (Threads.@threads over independent buffers) run
+// side by side instead of queueing on one mutex; a lane is created the first time every existing one is busy.
+// Device selection: snappy_b200_init(d >= 0) binds the CALLING THREAD to device d; an unbound thread uses
+// $SNAPPY_B200_DEVICE if set, else its current CUDA device (cudaGetDevice), which is what torch's
+// `with torch.cuda.device(...)` sets.  Device pointers passed to a call must belong to that device.
+constexpr int kMaxDevices = 16;
+constexpr int kMaxLanes = 4;
+struct DeviceSlot {
+    std::mutex mu;               // guards lanes[] / nlanes / once
+    std::mutex big;              // one streamed host pipeline (persistent kernels gated on copies) at a time
+    Context* lanes[kMaxLanes] = {};
+    int nlanes = 0;
+    bool once = false;           // per-device one-time setup done (L2 set-aside, probe-offset table)
+};
+DeviceSlot g_dev[kMaxDevices];
+thread_local int tl_device = -1;          // snappy_b200_init(d): this thread's device
+thread_local Context* tl_last = nullptr;  // the context of this thread's last call (last_kernel_ms / launch_count)
 
 int fail_cuda(cudaError_t e, const char* what) {
     char buf[256];
@@ -119,106 +148,63 @@ int fail_cuda(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
 
-// tuning knobs (snappy_b200_set_option / SNAPPY_B200_OPTIONS); caller holds the context mutex
+// tuning knobs (snappy_b200_set_option / SNAPPY_B200_OPTIONS); caller holds g_opt_mu
 void apply_option(const char* name, int value) {
     if (!name) return;
-    if (!strcmp(name, "compress_variant")) g_ctx.opt.compress_variant = value;
-    else if (!strcmp(name, "decode_variant")) g_ctx.opt.decode_variant = value;
-    else if (!strcmp(name, "smem_chains")) g_ctx.opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
-    else if (!strcmp(name, "l2_chains")) g_ctx.opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
-    else if (!strcmp(name, "l2_chains_big")) g_ctx.opt.l2_chains_big = value < 0 ? 0 : (value > 20 ? 20 : value);
-    else if (!strcmp(name, "spec_smem")) g_ctx.opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
-    else if (!strcmp(name, "spec_l2")) g_ctx.opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
+    if (!strcmp(name, "decode_variant")) g_opt.decode_variant = value;
+#ifdef SB200_EXPERIMENTS  // kernel designs that were measured and lost: not in the product build
+    else if (!strcmp(name, "compress_variant")) g_opt.compress_variant = value;
+    else if (!strcmp(name, "slowcont")) g_opt.slowcont = value != 0;
+    else if (!strcmp(name, "window")) g_opt.window = value;
+    else if (!strcmp(name, "wide")) g_opt.wide = value;
+#endif
+    else if (!strcmp(name, "smem_chains")) g_opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
+    else if (!strcmp(name, "l2_chains")) g_opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
+    else if (!strcmp(name, "l2_chains_big")) g_opt.l2_chains_big = value < 0 ? 0 : (value > 20 ? 20 : value);
+    else if (!strcmp(name, "spec_smem")) g_opt.spec_smem = value < 1 ? 1 : (value > 14 ? 14 : value);
+    else if (!strcmp(name, "spec_l2")) g_opt.spec_l2 = value < 1 ? 1 : (value > 14 ? 14 : value);
     else if (!strcmp(name, "ring_smem") || !strcmp(name, "ring_l2")) {
         int r = 1024;
         while (r < value && r < 32768) r <<= 1;
-        (name[5] == 's' ? g_ctx.opt.ring_smem : g_ctx.opt.ring_l2) = r;
+        (name[5] == 's' ? g_opt.ring_smem : g_opt.ring_l2) = r;
     }
-    else if (!strcmp(name, "parse_chunk_log2")) g_ctx.opt.parse_chunk_log2 = value < 9 ? 9 : (value > 16 ? 16 : value);
-    else if (!strcmp(name, "l2_persist")) g_ctx.opt.l2_persist = value;
-    else if (!strcmp(name, "overlap_compact")) g_ctx.opt.overlap_compact = value;
-    else if (!strcmp(name, "uncompress_segments")) g_ctx.opt.uncompress_segments = value;
-    else if (!strcmp(name, "dbg_skip_emit")) {
+    else if (!strcmp(name, "parse_chunk_log2")) g_opt.parse_chunk_log2 = value < 9 ? 9 : (value > 16 ? 16 : value);
+    else if (!strcmp(name, "l2_persist")) g_opt.l2_persist = value;
+    else if (!strcmp(name, "overlap_compact")) g_opt.overlap_compact = value;
+    else if (!strcmp(name, "uncompress_segments")) g_opt.uncompress_segments = value;
+#ifdef SB200_EXPERIMENTS
+    else if (!strcmp(name, "dbg_skip_emit")) {  // applies to the calling thread's current device
         const u32 v = (u32)value;
         cudaMemcpyToSymbol(g_dbg_skip_emit, &v, 4);
     }
-    else if (!strcmp(name, "rules")) g_ctx.opt.rules = value < 0 ? 0 : (value > 2 ? 2 : value);
-    else if (!strcmp(name, "slowcont")) g_ctx.opt.slowcont = value != 0;
-    else if (!strcmp(name, "window")) g_ctx.opt.window = value;
-    else if (!strcmp(name, "wide")) g_ctx.opt.wide = value;
-    else if (!strcmp(name, "l2_ctas")) g_ctx.opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
-    else if (!strcmp(name, "l2_reserve")) g_ctx.opt.l2_reserve = value;
-    else if (!strcmp(name, "host_pipeline")) g_ctx.opt.host_pipeline = value;
+#endif
+    else if (!strcmp(name, "rules")) g_opt.rules = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (!strcmp(name, "l2_ctas")) g_opt.l2_ctas = value < 1 ? 1 : (value > 3 ? 3 : value);
+    else if (!strcmp(name, "l2_reserve")) g_opt.l2_reserve = value;
+    else if (!strcmp(name, "host_pipeline")) g_opt.host_pipeline = value;
     else if (!strcmp(name, "pipe_chunk_frags")) {
         // at most kMaxPipeChunks chunks for the largest stream (2^32 bytes = 65536 fragments)
-        g_ctx.opt.pipe_chunk_frags = value < 1024 ? 1024 : value;
+        g_opt.pipe_chunk_frags = value < 1024 ? 1024 : value;
     }
-    else if (!strcmp(name, "decode_occupancy")) g_ctx.opt.decode_occupancy = value;
-    else if (!strcmp(name, "timing")) g_ctx.opt.timing = value;
+    else if (!strcmp(name, "decode_occupancy")) g_opt.decode_occupancy = value;
+    else if (!strcmp(name, "timing")) g_opt.timing = value;
+    else if (!strcmp(name, "lpt")) g_opt.lpt = value;
+    else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
 }
 
-int ctx_init_locked(int device) {
-    Context& c = g_ctx;
-    if (c.ready) return SNAPPY_B200_OK;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
-        return SNAPPY_B200_NO_DEVICE;
-    }
-    if (device < 0) {
-        const char* env = getenv("SNAPPY_B200_DEVICE");
-        if (env) {
-            device = atoi(env);
-        } else if (cudaGetDevice(&device) != cudaSuccess) {
-            device = 0;
-        }
-    }
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        char buf[128];
-        snprintf(buf, sizeof buf, "device %d is sm_%d%d; libsnappy_b200 holds sm_100a code only", device,
-                 prop.major, prop.minor);
-        g_last_error = buf;
-        return SNAPPY_B200_NO_DEVICE;
-    }
-    c.device = device;
-    c.sm_count = prop.multiProcessorCount;
-    // L2 set-aside for persisting / evict_last lines, at its maximum (79 MiB on B200): the global hash tables of
-    // the global-table compress warps are read and written with L2::evict_last hints and live there (13.2 ms with
-    // the set-aside, 14.1 ms without; SNAPPY_B200_NO_PERSIST_LIMIT=1 leaves the device default)
-    c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-    c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (c.l2_persist_max && !getenv("SNAPPY_B200_NO_PERSIST_LIMIT")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max);
-    if (getenv("SNAPPY_B200_DEBUG"))
-        fprintf(stderr, "[snappy_b200] L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", prop.l2CacheSize >> 20,
-                c.l2_persist_max >> 20, c.l2_window_max >> 20);
-    CU(cudaFuncSetAttribute(k_compress_fragments_serial, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kCompressSmemBytes));
+// Shared-memory opt-ins of the kernels (per device; the attributes live in the device's module).
+int set_kernel_attributes() {
     CU(cudaFuncSetAttribute(k_compress_pages<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompressSmemBytes));
     CU(cudaFuncSetAttribute(k_compress_pages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kCompressSmemBytes + kMaxTableEntries * 2)));
-    CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kCompress2SmemBytes));
-    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    // both kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
+    // both window kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
     // CTAs fit next to the shared-table CTA
-    CU(cudaFuncSetAttribute(k_compress_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaFuncSetAttribute(k_compress_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -226,30 +212,58 @@ int ctx_init_locked(int device) {
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
+#ifdef SB200_EXPERIMENTS
+    CU(cudaFuncSetAttribute(k_compress_fragments_serial, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompressSmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_fragments, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompress2SmemBytes));
+    CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_chain<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_chain<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
-    k_init_probe_offsets<<<1, 32>>>();
-    CU(cudaGetLastError());
-    CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c.s_pack, cudaStreamNonBlocking));
-    for (int i = 0; i < kMaxPipeChunks; i++) {
-        CU(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+#endif
+    return SNAPPY_B200_OK;
+}
+
+// Resolve the device a call on this thread addresses (see DeviceSlot above).
+int resolve_device(int* device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return SNAPPY_B200_NO_DEVICE;
     }
-    CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
-    CU(cudaMallocHost(&c.pinned, 4096));
-    CU(cudaMallocHost(&c.pinned_zero, kTailPad));
-    memset(c.pinned_zero, 0, kTailPad);
-    for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
-    CU(c.result.ensure(256));
-    c.ready = true;
+    int d = tl_device;
+    if (d < 0) {
+        const char* env = getenv("SNAPPY_B200_DEVICE");
+        if (env) d = atoi(env);
+        else if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    }
+    if (d < 0 || d >= count || d >= kMaxDevices) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "device %d does not exist (%d CUDA devices)", d, count);
+        g_last_error = buf;
+        return SNAPPY_B200_BAD_ARGUMENT;
+    }
+    *device = d;
+    return SNAPPY_B200_OK;
+}
+
+void parse_env_options() {
     // tuning knobs from the environment: SNAPPY_B200_OPTIONS="name=value,name=value" (see set_option)
+    static bool done = false;
+    std::unique_lock<std::mutex> lk(g_opt_mu);
+    if (done) return;
+    done = true;
     if (const char* env = getenv("SNAPPY_B200_OPTIONS")) {
         std::string e(env);
         size_t pos = 0;
@@ -262,7 +276,94 @@ int ctx_init_locked(int device) {
             pos = comma + 1;
         }
     }
+}
+
+void ctx_destroy(Context& c);
+
+// Create the streams, events and pinned areas of a lane (current device == `device`); slot.mu is held.
+int ctx_init(Context& c, int device, DeviceSlot& slot) {
+    if (c.ready) return SNAPPY_B200_OK;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; libsnappy_b200 holds sm_100a code only", device,
+                 prop.major, prop.minor);
+        g_last_error = buf;
+        return SNAPPY_B200_NO_DEVICE;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c.l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (!slot.once) {
+        // L2 set-aside for persisting / evict_last lines, at its maximum (79 MiB on B200): the global hash tables
+        // of the global-table compress warps are read and written with L2::evict_last hints and live there
+        // (13.2 ms with the set-aside, 14.1 ms without; SNAPPY_B200_NO_PERSIST_LIMIT=1 leaves the device default)
+        if (c.l2_persist_max && !getenv("SNAPPY_B200_NO_PERSIST_LIMIT"))
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.l2_persist_max);
+        if (getenv("SNAPPY_B200_DEBUG"))
+            fprintf(stderr, "[snappy_b200] device %d: L2 %d MiB, persisting max %zu MiB, window max %zu MiB\n", device,
+                    prop.l2CacheSize >> 20, c.l2_persist_max >> 20, c.l2_window_max >> 20);
+        int rc = set_kernel_attributes();
+        if (rc != SNAPPY_B200_OK) return rc;
+        k_init_probe_offsets<<<1, 32>>>();
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+        slot.once = true;
+    }
+    // a failure below leaves a half-built lane: release what exists, so that a retry starts clean
+    struct Guard {
+        Context& c;
+        bool armed = true;
+        ~Guard() { if (armed) ctx_destroy(c); }
+    } guard{c};
+    CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_pack, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxPipeChunks; i++) {
+        CU(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    CU(cudaMallocHost(&c.pinned, kPinnedBytes));
+    CU(cudaMallocHost(&c.pinned_zero, kTailPad));
+    memset(c.pinned_zero, 0, kTailPad);
+    for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
+    CU(c.result.ensure(256));
+    guard.armed = false;
+    c.ready = true;
     return SNAPPY_B200_OK;
+}
+
+// Release everything a lane owns (current device == c.device).
+void ctx_destroy(Context& c) {
+    for (cudaStream_t* sp : {&c.side, &c.s_h2d, &c.s_d2h, &c.s_comp, &c.s_pack}) {
+        if (*sp) cudaStreamDestroy(*sp);
+        *sp = nullptr;
+    }
+    for (int i = 0; i < kMaxPipeChunks; i++) {
+        if (c.ev_in[i]) cudaEventDestroy(c.ev_in[i]);
+        if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
+        c.ev_in[i] = c.ev_done[i] = nullptr;
+    }
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    c.ev_fork = c.ev_join = nullptr;
+    for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a,
+                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order})
+        b->release();
+    if (c.pinned) cudaFreeHost(c.pinned);
+    if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
+    c.pinned = c.pinned_zero = nullptr;
+    for (auto& ev : c.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    c.ready = false;
 }
 
 // collect the event pair recorded around the dominant kernel of the last call
@@ -274,6 +375,9 @@ void harvest_timing(Context& c, int which) {
         c.ev_pending[which] = false;
     }
 }
+
+// fragments of an n-byte stream; in 64 bits: (u32)n + 65535 wraps for streams within 64 KiB of 4 GiB
+inline u32 frag_count(u64 n) { return (u32)((n + kBlockSize - 1) / kBlockSize); }
 
 inline u32 table_shift(u64 total_len) {
     u32 entries = 256;  // alloc_hashtable, src/internal.jl:107-113
@@ -345,6 +449,19 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     }
     u32* counter = (u32*)((u8*)c.result.p + 64);
     CU(cudaMemsetAsync(counter, 0, 4, st));
+    // fragment order: expensive first (schedule.cuh).  Not for the streamed host path (fragments become resident
+    // in stream order) and pointless below a few fragments per warp.
+    const u32* order = nullptr;
+    if (c.opt.lpt && !gate && nfrag >= 2u * (u32)c.sm_count) {
+        CU(c.order.ensure((size_t)nfrag * 5));
+        u32* ord = (u32*)c.order.p;
+        u8* cost = (u8*)(ord + nfrag);
+        k_estimate_cost<<<(nfrag + kCostWarps - 1) / kCostWarps, kCostWarps * 32, 0, st>>>(d_in, (u64)len, nfrag, descs,
+                                                                                         ndesc, cost);
+        k_order_by_cost<<<1, 1024, 0, st>>>(cost, nfrag, ord);
+        *launches += 2;
+        order = ord;
+    }
     // one CTA per SM, smem_chains warps each (fewer CTAs when there are fewer fragments)
     // rules != 0 (libsnappy's emission rules): always the window kernel, compiled with kLib; rules = 2 has
     // 64 KiB tables, so 3 shared-table warps per SM (and l2_chains_big global-table warps)
@@ -364,6 +481,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     const u32 ctas_b = (wb && (nfrag > warps_a + reserve || !wa)) ? (u32)(c.sm_count * c.opt.l2_ctas) : 0u;
     if (ctas_b) CU(c.gtables.ensure((size_t)ctas_b * wb * tab_bytes));
     if (ctas_b) CU(cudaEventRecord(c.ev_fork, st));
+#ifdef SB200_EXPERIMENTS
     if (!rules && (c.opt.wide == 2 || c.opt.wide == 4)) {  // kW warps per fragment, shared tables only
         const u32 chains = (u32)c.opt.smem_chains, ra = (u32)c.opt.ring_smem;
         u32 ctas = (nfrag + chains - 1) / chains;
@@ -377,25 +495,29 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         *launches += 1;
         return SNAPPY_B200_OK;
     }
+#endif
     const bool window = c.opt.window != 0 || rules != 0;
+    (void)window;
     const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
     if (ctas_a) {
         if (rules)
             k_compress_window<true, true><<<ctas_a, wa * 32, (size_t)wa * (tab_bytes + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules);
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules, order);
+#ifdef SB200_EXPERIMENTS
         else if (window && c.opt.slowcont)
             k_compress_window<true, false, true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
                 ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
-        else if (window)
-            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
-        else
+        else if (!window)
             k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
                 (u32)c.opt.spec_smem, 0u, descs, ndesc);
+#endif
+        else
+            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, 0u, order);
     }
     *launches += 1;
     if (ctas_b) {
@@ -418,21 +540,23 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             k_compress_window<false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u, rules);
+                gate ? gate->div : 1u, rules, order);
+#ifdef SB200_EXPERIMENTS
         else if (window && c.opt.slowcont)
             k_compress_window<false, false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
                 gate ? gate->div : 1u);
-        else if (window)
-            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
-                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u);
-        else
+        else if (!window)
             k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
                 (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
+#endif
+        else
+            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
+                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
+                gate ? gate->div : 1u, 0u, order);
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -522,7 +646,9 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
         int rc = launch_chain_kernels(c, d_in, shard_len, shift, scratch, sizes, st, &launches);
         if (rc != SNAPPY_B200_OK) return rc;
-    } else {
+    }
+#ifdef SB200_EXPERIMENTS
+    else {
         if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
         if (c.opt.compress_variant == 1)
             k_compress_fragments_serial<<<nfrag, 32, kCompressSmemBytes, st>>>(d_in, (u64)shard_len, shift,
@@ -532,6 +658,7 @@ int compress_shard_locked(Context& c, const u8* d_in, size_t shard_len, u64 tota
                                                                         scratch, sizes);
         launches = 1;
     }
+#endif
     if (c.opt.timing) {
         CU(cudaEventRecord(c.ev[1], st));
         c.ev_pending[0] = true;
@@ -586,7 +713,7 @@ int decode_exact_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_
 // the events used).  No synchronisation.
 int decode_launch(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed, const u64* d_index,
                   cudaStream_t st, u32 fa, u32 fb, u8* host_out, int* ri, u32 range = 0) {
-    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    const u32 nfrag = frag_count(claimed);
     DecodeResult* res = (DecodeResult*)c.result.p;
     const bool ranged = host_out != nullptr;
     const u32 step = ranged ? (range ? range : (u32)c.opt.pipe_chunk_frags) : (fb - fa);
@@ -637,7 +764,7 @@ int decode_finish(Context& c, cudaStream_t st, bool ranged) {
 int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed,
                           const u64* d_index, cudaStream_t st, u8* host_out = nullptr,
                           bool* host_copied = nullptr) {
-    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    const u32 nfrag = frag_count(claimed);
     if (nfrag == 0) return -1;
     CU(cudaMemsetAsync(c.result.p, 0, sizeof(DecodeResult), st));
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
@@ -720,7 +847,7 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
 
 // The whole stream as one segment.
 int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 claimed, cudaStream_t st) {
-    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    const u32 nfrag = frag_count(claimed);
     if (nfrag == 0 || n <= hdr) return -1;
     u64 ex = 0, total = 0;
     const int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total);
@@ -762,14 +889,60 @@ int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, si
     return decode_exact_locked(c, d_in, n, hdr, d_out, claimed, st);
 }
 
+// Takes a lane of the addressed device for the duration of a call: resolves the device, makes it current (the
+// caller's current device is restored on exit), picks a free lane or creates one.
 struct Locked {
     std::unique_lock<std::mutex> lk;
-    int rc;
-    Locked() : lk(g_ctx.mu), rc(ctx_init_locked(-1)) {
-        if (rc == SNAPPY_B200_OK) {
-            cudaError_t e = cudaSetDevice(g_ctx.device);
-            if (e != cudaSuccess) rc = fail_cuda(e, "cudaSetDevice");
+    Context* c = nullptr;
+    int rc = SNAPPY_B200_OK;
+    int prev_device = -1;
+    Locked() {
+        parse_env_options();
+        int d = -1;
+        rc = resolve_device(&d);
+        if (rc != SNAPPY_B200_OK) return;
+        cudaGetDevice(&prev_device);
+        cudaError_t e = cudaSetDevice(d);
+        if (e != cudaSuccess) {
+            rc = fail_cuda(e, "cudaSetDevice");
+            return;
         }
+        DeviceSlot& slot = g_dev[d];
+        {
+            std::unique_lock<std::mutex> sl(slot.mu);
+            for (int i = 0; i < slot.nlanes && !c; i++) {
+                std::unique_lock<std::mutex> t(slot.lanes[i]->mu, std::try_to_lock);
+                if (t.owns_lock()) {
+                    lk = std::move(t);
+                    c = slot.lanes[i];
+                }
+            }
+            if (!c && slot.nlanes < kMaxLanes) {
+                Context* n = new Context();
+                n->lane = slot.nlanes;
+                lk = std::unique_lock<std::mutex>(n->mu);
+                rc = ctx_init(*n, d, slot);
+                if (rc != SNAPPY_B200_OK) {
+                    lk.unlock();
+                    lk = std::unique_lock<std::mutex>();
+                    delete n;
+                    return;
+                }
+                slot.lanes[slot.nlanes++] = n;
+                c = n;
+            }
+        }
+        if (!c) {  // every lane is busy: wait for one (spread the waiters over the lanes)
+            static std::atomic<unsigned> turn{0};
+            Context* w = g_dev[d].lanes[turn.fetch_add(1) % kMaxLanes];
+            lk = std::unique_lock<std::mutex>(w->mu);
+            c = w;
+        }
+        tl_last = c;
+    }
+    ~Locked() {
+        if (lk.owns_lock()) lk.unlock();
+        if (prev_device >= 0) cudaSetDevice(prev_device);
     }
 };
 
@@ -798,40 +971,48 @@ const char* snappy_b200_status_string(int status) {
 const char* snappy_b200_last_error(void) { return g_last_error.c_str(); }
 
 int snappy_b200_init(int device) {
-    std::unique_lock<std::mutex> lk(g_ctx.mu);
-    return ctx_init_locked(device);
+    // device >= 0: bind the calling thread to that device; < 0: unbind (current CUDA device / $SNAPPY_B200_DEVICE)
+    if (device >= 0) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+            return SNAPPY_B200_NO_DEVICE;
+        }
+        if (device >= count || device >= kMaxDevices) {
+            char buf[96];
+            snprintf(buf, sizeof buf, "device %d does not exist (%d CUDA devices)", device, count);
+            g_last_error = buf;
+            return SNAPPY_B200_BAD_ARGUMENT;
+        }
+    }
+    tl_device = device < 0 ? -1 : device;
+    Locked L;  // creates the first lane of the device (checks that it is an sm_100 part)
+    return L.rc;
 }
 
 void snappy_b200_shutdown(void) {
-    std::unique_lock<std::mutex> lk(g_ctx.mu);
-    Context& c = g_ctx;
-    if (!c.ready) return;
-    cudaSetDevice(c.device);
-    if (c.side) cudaStreamDestroy(c.side);
-    c.side = nullptr;
-    for (cudaStream_t* sp : {&c.s_h2d, &c.s_d2h, &c.s_comp}) {
-        if (*sp) cudaStreamDestroy(*sp);
-        *sp = nullptr;
+    // releases every lane of every device; callers must not be inside another entry point
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < kMaxDevices; d++) {
+        DeviceSlot& slot = g_dev[d];
+        std::unique_lock<std::mutex> sl(slot.mu);
+        if (!slot.nlanes) continue;
+        cudaSetDevice(d);
+        for (int i = 0; i < slot.nlanes; i++) {
+            {
+                std::unique_lock<std::mutex> lk(slot.lanes[i]->mu);
+                ctx_destroy(*slot.lanes[i]);
+            }
+            if (tl_last == slot.lanes[i]) tl_last = nullptr;
+            delete slot.lanes[i];
+            slot.lanes[i] = nullptr;
+        }
+        slot.nlanes = 0;
+        slot.once = false;
     }
-    for (int i = 0; i < kMaxPipeChunks; i++) {
-        if (c.ev_in[i]) cudaEventDestroy(c.ev_in[i]);
-        if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
-        c.ev_in[i] = c.ev_done[i] = nullptr;
-    }
-    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
-    if (c.ev_join) cudaEventDestroy(c.ev_join);
-    c.ev_fork = c.ev_join = nullptr;
-    for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a, &c.parse_b,
-                      &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags})
-        b->release();
-    if (c.pinned) cudaFreeHost(c.pinned);
-    if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
-    c.pinned = c.pinned_zero = nullptr;
-    for (auto& ev : c.ev) {
-        if (ev) cudaEventDestroy(ev);
-        ev = nullptr;
-    }
-    c.ready = false;
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 size_t snappy_b200_max_compressed_length(size_t n) { return 32 + n + n / 6; }  // src/Snappy.jl:80-82
@@ -874,7 +1055,7 @@ int snappy_b200_compress_device(const uint8_t* d_in, size_t n, uint8_t* d_out, s
     if (!out_len || (!d_in && n) || !d_out) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    return compress_device_locked(g_ctx, d_in, n, d_out, out_cap, out_len, (u64*)d_frag_index,
+    return compress_device_locked(*L.c, d_in, n, d_out, out_cap, out_len, (u64*)d_frag_index,
                                   (cudaStream_t)stream);
 }
 
@@ -883,9 +1064,21 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
     if (!out_len || (!d_in && n)) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    return uncompress_device_locked(g_ctx, d_in, n, d_out, out_cap, out_len, (const u64*)d_frag_index,
+    return uncompress_device_locked(*L.c, d_in, n, d_out, out_cap, out_len, (const u64*)d_frag_index,
                                     (cudaStream_t)stream);
 }
+
+// The streamed host paths enqueue copies from / into the CALLER's buffers on several streams.  Whatever way such a
+// function returns, nothing may still be in flight: an early error return drains the pipeline first.
+struct PipeGuard {
+    Context& c;
+    bool drained = false;
+    ~PipeGuard() {
+        if (drained) return;
+        for (cudaStream_t st : {c.s_h2d, c.s_comp, c.side, c.s_pack, c.s_d2h})
+            if (st) cudaStreamSynchronize(st);
+    }
+};
 
 // Host-buffer compress, streamed: ONE launch of the persistent compress kernels
 // covers the whole input.  The input goes up in chunks on a copy stream, each followed by a 4-byte
@@ -895,6 +1088,7 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
 // third stream while the rest still compresses.  Only the running stream length (8 bytes per chunk)
 // is read by the host.
 int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* out_len) {
+    PipeGuard guard{c};
     const size_t cf = 1024;  // fragments per chunk (64 MiB up, ~30 MB down)
     const size_t need = snappy_b200_max_compressed_length(n);
     const u32 nfrag = (u32)((n + kBlockSize - 1) / kBlockSize);
@@ -981,6 +1175,7 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
     harvest_timing(c, 0);
     c.last_launches[0] = launches;
     *out_len = (size_t)prev;
+    guard.drained = true;
     return SNAPPY_B200_OK;
 }
 
@@ -989,6 +1184,7 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
 // previous one's bytes as soon as it has landed, and its bytes go back down on a third stream
 // while the next chunk compresses.  Only the chunk totals (8 bytes each) are read by the host.
 int compress_host_pipelined(Context& c, const u8* in, size_t n, u8* out, size_t* out_len) {
+    PipeGuard guard{c};
     const size_t kPipeChunkFrags = (size_t)c.opt.pipe_chunk_frags;
     const size_t need = snappy_b200_max_compressed_length(n);
     const u32 nfrag = (u32)((n + kBlockSize - 1) / kBlockSize);
@@ -1055,7 +1251,7 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
     if (*out_len < need) return SNAPPY_B200_BUFFER_TOO_SMALL;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     if (c.opt.compress_variant == 0 && c.opt.host_pipeline == 1 && c.opt.window && !c.opt.wide &&
         n > (size_t)2048 * kBlockSize)
         return compress_host_streamed(c, in, n, out, out_len);
@@ -1081,9 +1277,10 @@ int snappy_b200_compress(const uint8_t* in, size_t n, uint8_t* out, size_t* out_
 // segment is still on its way up.  Returns -1 when the stream needs the whole-stream paths (not
 // fragment-clean, anomalies): the caller then runs them on the resident copy.
 int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32 claimed, u8* out) {
+    PipeGuard guard{c};
     const int kChunks = 16;
     const int kSegs = (c.opt.uncompress_segments == 2 || c.opt.uncompress_segments == 8) ? c.opt.uncompress_segments : 4;
-    const u32 nfrag = (claimed + kBlockSize - 1) / kBlockSize;
+    const u32 nfrag = frag_count(claimed);
     cudaStream_t st = c.s_comp;
     u8* d_in = (u8*)c.stage_in.p;
     u8* d_out = (u8*)c.stage_out.p;
@@ -1166,7 +1363,7 @@ int snappy_b200_uncompress(const uint8_t* in, size_t n, uint8_t* out, size_t* ou
     if (*out_len < claimed) return SNAPPY_B200_BUFFER_TOO_SMALL;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     CU(c.stage_in.ensure(n + 16));
     CU(c.stage_out.ensure((size_t)claimed + 16));
     cudaStream_t st = c.s_comp;
@@ -1203,7 +1400,7 @@ int snappy_b200_compress_shard_device(const uint8_t* d_shard, size_t shard_len, 
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
     u64 total = 0;
-    int rc = compress_shard_locked(g_ctx, d_shard, shard_len, total_len, d_out, 0, &total, nullptr,
+    int rc = compress_shard_locked(*L.c, d_shard, shard_len, total_len, d_out, 0, &total, nullptr,
                                    d_frag_sizes, (cudaStream_t)stream);
     if (rc == SNAPPY_B200_OK) *out_len = (size_t)total;
     return rc;
@@ -1216,7 +1413,7 @@ int snappy_b200_uncompress_shard_device(const uint8_t* d_in, const uint64_t* d_f
     if (nfrag == 0) return SNAPPY_B200_OK;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     cudaStream_t st = (cudaStream_t)stream;
     c.last_launches[1] = 0;
     // the shard's own first/last offsets bound its element bytes
@@ -1278,7 +1475,7 @@ int snappy_b200_compress_shards_device(const uint8_t* const* d_shards, const siz
     if (nfrag_total > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     cudaStream_t st = (cudaStream_t)stream;
     const u32 nd = (u32)descs.size();
     CU(c.tail.ensure(kTailSlot * nd));
@@ -1305,8 +1502,7 @@ int snappy_b200_compress_shards_device(const uint8_t* const* d_shards, const siz
         CU(cudaEventRecord(c.ev[1], st));
         c.ev_pending[0] = true;
     }
-    u64* h = (u64*)((u8*)c.pinned + 2048);
-    if (nd > 200) return SNAPPY_B200_BAD_ARGUMENT;  // pinned readback area
+    u64* h = (u64*)((u8*)c.pinned + kPinnedShardLens);  // count <= 4096 checked on entry
     for (u32 i = 0; i < nd; i++) {
         const u32 fb = descs[i].frag_begin, nf = descs[i].nfrag;
         u64* o = offs + fb + i;  // nf + 1 entries per shard
@@ -1350,7 +1546,7 @@ int snappy_b200_uncompress_shards_device(const uint8_t* const* d_ins, const uint
     if (nfrag_total > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     cudaStream_t st = (cudaStream_t)stream;
     const u32 nd = (u32)descs.size();
     CU(c.descs.ensure(sizeof(DecodeDesc) * nd));
@@ -1385,7 +1581,7 @@ int snappy_b200_compress_batched_device(const uint8_t* d_in, const uint64_t* d_i
     if (count > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     cudaStream_t st = (cudaStream_t)stream;
     // the largest page decides the shared-memory footprint (fragment buffer + table)
     u32* d_max = (u32*)c.result.p;
@@ -1431,7 +1627,7 @@ int snappy_b200_uncompress_batched_device(const uint8_t* d_in, const uint64_t* d
     if (count > 0x7fffffffull) return SNAPPY_B200_BAD_ARGUMENT;
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
-    Context& c = g_ctx;
+    Context& c = *L.c;
     cudaStream_t st = (cudaStream_t)stream;
     if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
     const unsigned grid = (unsigned)((count + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta);
@@ -1450,8 +1646,8 @@ int snappy_b200_uncompress_batched_device(const uint8_t* d_in, const uint64_t* d
 }
 
 float snappy_b200_last_kernel_ms(int which) {
-    std::unique_lock<std::mutex> lk(g_ctx.mu);
-    return (which == 0 || which == 1) ? g_ctx.last_ms[which] : 0.f;
+    Context* c = tl_last;  // the lane this thread's last call ran on
+    return (c && (which == 0 || which == 1)) ? c->last_ms[which] : 0.f;
 }
 
 // ---- side-index sidecar (host only) ---------------------------------------------------------
@@ -1533,13 +1729,41 @@ int snappy_b200_index_unpack(const uint8_t* in, size_t n, uint64_t* index, size_
 }
 
 int snappy_b200_last_launch_count(int which) {
-    std::unique_lock<std::mutex> lk(g_ctx.mu);
-    return (which == 0 || which == 1) ? g_ctx.last_launches[which] : 0;
+    Context* c = tl_last;
+    return (c && (which == 0 || which == 1)) ? c->last_launches[which] : 0;
 }
 
 
+int snappy_b200_get_option(const char* name) {
+    if (!name) return -1;
+    parse_env_options();
+    std::unique_lock<std::mutex> lk(g_opt_mu);
+    const Options& o = g_opt;
+    if (!strcmp(name, "experiments")) {
+#ifdef SB200_EXPERIMENTS
+        return 1;
+#else
+        return 0;
+#endif
+    }
+    const struct { const char* n; int v; } tab[] = {
+        {"rules", o.rules}, {"smem_chains", o.smem_chains}, {"l2_chains", o.l2_chains},
+        {"l2_chains_big", o.l2_chains_big}, {"l2_ctas", o.l2_ctas}, {"l2_reserve", o.l2_reserve},
+        {"ring_smem", o.ring_smem}, {"ring_l2", o.ring_l2}, {"decode_variant", o.decode_variant},
+        {"decode_occupancy", o.decode_occupancy}, {"pipe_chunk_frags", o.pipe_chunk_frags},
+        {"parse_chunk_log2", o.parse_chunk_log2}, {"uncompress_segments", o.uncompress_segments},
+        {"host_pipeline", o.host_pipeline}, {"timing", o.timing}, {"l2_persist", o.l2_persist},
+        {"overlap_compact", o.overlap_compact}, {"window", o.window}, {"wide", o.wide}, {"slowcont", o.slowcont},
+        {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host},
+    };
+    for (const auto& e : tab)
+        if (!strcmp(name, e.n)) return e.v;
+    return -1;
+}
+
 void snappy_b200_set_option(const char* name, int value) {
-    std::unique_lock<std::mutex> lk(g_ctx.mu);
+    parse_env_options();
+    std::unique_lock<std::mutex> lk(g_opt_mu);
     apply_option(name, value);
 }
 

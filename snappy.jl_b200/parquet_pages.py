@@ -144,6 +144,17 @@ def list_pages(file_bytes):
                     h2 = f[8]
                     prefix = h2.get(5, 0) + h2.get(6, 0)       # definition + repetition level bytes
                     compressed = h2.get(7, True)
+                # the sizes come from the file: nothing below may let the decode kernel read past the image or
+                # take a negative / >= 2 GiB length (in_sizes and out_caps are 32-bit in the batched C ABI)
+                if not isinstance(prefix, int) or not (0 <= prefix <= csize and prefix <= usize):
+                    raise ValueError("page at %d: level bytes (%r) exceed the page sizes (%d compressed, %d "
+                                     "uncompressed)" % (pos, prefix, csize, usize))
+                if csize >= 1 << 31 or usize >= 1 << 31:
+                    raise ValueError("page at %d: size of 2 GiB or more (%d compressed, %d uncompressed)"
+                                     % (pos, csize, usize))
+                if body + csize > len(buf):
+                    raise ValueError("page at %d: body [%d, %d) runs past the end of the file image (%d bytes)"
+                                     % (pos, body, body + csize, len(buf)))
                 pages.append({"codec": col.compression if compressed else "UNCOMPRESSED", "kind": kind,
                               "header": pos, "body": body, "prefix": prefix, "stream": body + prefix,
                               "compressed": csize - prefix, "uncompressed": usize - prefix})
@@ -160,6 +171,11 @@ def uncompress_pages(file_bytes, pages=None):
     if pages is None:
         pages = list_pages(file_bytes)
     sel = [p for p in pages if p["codec"] == SNAPPY and p["compressed"] > 0]
+    for p in sel:  # a caller-supplied page list gets the same checks as list_pages applies
+        if not (0 <= p["stream"] and p["stream"] + p["compressed"] <= len(file_bytes) and
+                0 <= p["uncompressed"] < 1 << 31 and p["compressed"] < 1 << 31):
+            raise ValueError("page stream [%d, +%d) -> %d bytes does not fit the file image (%d bytes)"
+                             % (p["stream"], p["compressed"], p["uncompressed"], len(file_bytes)))
     offs = np.full(len(pages), -1, dtype=np.int64)
     if not sel:
         return pages, np.empty(0, dtype=np.uint8), offs

@@ -2,11 +2,12 @@
 (host-buffer and device-resident entry points) and is compared with the CPU oracle on the same
 inputs -- bit-exact, both directions."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
 
-from conftest import (ALL_FILES, corrupt_streams, dictionary_fuzz, edge_inputs, read_data)
+from conftest import (ALL_FILES, ROOT, corrupt_streams, dictionary_fuzz, edge_inputs, read_data)
 
 pytestmark = pytest.mark.gpu
 
@@ -297,23 +298,25 @@ def test_batched_shard_api(dev, oracle):
         assert np.array_equal(o.cpu().numpy(), streams[w][a:b])
 
 
+VARIANT_DEFAULTS = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6, "slowcont": 0, "lpt": 1}
+
+
+def _variant_input():
+    from snappy_jl_b200 import synth
+    return np.concatenate([synth.mix(96, seed=5, tail=777),
+                           np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
+                                         dtype=np.uint8)])
+
+
 @pytest.mark.parametrize("options", [
-    {"window": 0},                       # step-wise chain kernel (compress_chain.cuh)
-    {"window": 1, "l2_chains": 0},       # window kernel, shared-memory tables only
-    {"window": 1, "smem_chains": 0},     # window kernel, global tables only
-    {"window": 1, "wide": 4},            # 4 warps per fragment (compress_wide.cuh)
-    {"window": 1, "wide": 2},
-    {"window": 1, "slowcont": 1},        # long copies extended inside the hop loop (measured slower: off by default)
+    {"l2_chains": 0},       # window kernel, shared-memory tables only
+    {"smem_chains": 0},     # window kernel, global tables only
+    {"lpt": 0},             # fragments in stream order instead of expensive-first (schedule.cuh)
 ])
 def test_compress_kernel_variants_bit_exact(dev, oracle, options):
-    """every compress kernel in the library produces the oracle's bytes (the default is the window
-    kernel with both table placements running side by side)"""
-    import torch
-    from snappy_jl_b200 import synth
-    defaults = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6, "slowcont": 0}
-    raw = np.concatenate([synth.mix(96, seed=5, tail=777),
-                          np.frombuffer(read_data("alice29.txt") + read_data("html_x_4") + read_data("urls.10K"),
-                                        dtype=np.uint8)])
+    """every table placement / fragment order of the shipped compress kernel produces the oracle's bytes (the default
+    is both table placements side by side, fragments handed out expensive-first)"""
+    raw = _variant_input()
     want = oracle.compress_np(raw)
     try:
         for k, v in options.items():
@@ -321,9 +324,65 @@ def test_compress_kernel_variants_bit_exact(dev, oracle, options):
         stream, _ = dev.compress_device(to_dev(raw), want_index=False)
         got = stream.cpu().numpy()
     finally:
-        for k, v in defaults.items():
+        for k, v in VARIANT_DEFAULTS.items():
             dev.set_option(k, v)
     assert got.size == want.size and np.array_equal(got, want)
+
+
+def test_lpt_order_is_a_permutation_and_large_input_bit_exact(dev, oracle):
+    """enough fragments for the expensive-first order to engage (>= 2 per SM): bytes and side index unchanged"""
+    from snappy_jl_b200 import synth
+    raw = synth.mix(700, seed=91, tail=12345)
+    want = oracle.compress_np(raw)
+    stream, index = dev.compress_device(to_dev(raw), want_index=True)
+    assert np.array_equal(stream.cpu().numpy(), want)
+    idx = index.cpu().numpy()
+    assert idx[-1] == want.size and np.all(np.diff(idx) > 0)
+    try:
+        dev.set_option("lpt", 0)
+        stream2, index2 = dev.compress_device(to_dev(raw), want_index=True)
+    finally:
+        dev.set_option("lpt", 1)
+    assert np.array_equal(stream2.cpu().numpy(), want) and np.array_equal(index2.cpu().numpy(), idx)
+
+
+EXPERIMENT_SCRIPT = r"""
+import sys, json
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle"); sys.path.insert(0, %(root)r + "/tests")
+import numpy as np, torch, pyoracle
+import snappy_jl_b200 as S
+from snappy_jl_b200 import device as dev
+from test_gpu_parity import _variant_input
+assert S._abi.lib().snappy_b200_get_option(b"experiments") == 1
+raw = _variant_input()
+want = pyoracle.compress_np(raw)
+d = torch.from_numpy(raw).cuda()
+bad = []
+for options in ({"window": 0}, {"wide": 4}, {"wide": 2}, {"slowcont": 1}, {"compress_variant": 1}, {"compress_variant": 2}):
+    for k, v in options.items():
+        dev.set_option(k, v)
+    got = dev.compress_device(d)[0].cpu().numpy()
+    for k in options:
+        dev.set_option(k, {"window": 1}.get(k, 0))
+    if got.size != want.size or not np.array_equal(got, want):
+        bad.append(options)
+print("EXPERIMENTS_BAD", json.dumps(bad))
+"""
+
+
+def test_experimental_kernels_bit_exact():
+    """The designs that were measured and lost (step-wise chain kernel, 2/4 warps per fragment, slowcont, the two
+    TMA-staged first versions) live in libsnappy_b200_exp.so (make exp, -DSB200_EXPERIMENTS), not in the product
+    library; they stay byte-identical to the oracle."""
+    import subprocess
+    import sys
+    exp = os.path.join(ROOT, "snappy.jl_b200", "libsnappy_b200_exp.so")
+    if not os.path.exists(exp):
+        pytest.skip("libsnappy_b200_exp.so not built (make -C snappy.jl_b200/csrc exp)")
+    p = subprocess.run([sys.executable, "-c", EXPERIMENT_SCRIPT % {"root": ROOT}], capture_output=True, text=True,
+                       env=dict(os.environ, SNAPPY_B200_LIB=exp), timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "EXPERIMENTS_BAD []" in p.stdout, p.stdout
 
 
 def test_streamed_uncompress_foreign_and_corrupt(snappy, oracle):

@@ -21,7 +21,7 @@ def warp(tmp_path_factory):
     exe = str(d / "run_window_kernel")
     obj = str(d / "oracle.o")
     subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
                            "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_window_kernel.cpp"), obj])
     return exe
 
@@ -81,7 +81,7 @@ def decode_warp(tmp_path_factory):
     exe = str(d / "run_decode_kernel")
     obj = str(d / "oracle.o")
     subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
                            "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_decode_kernel.cpp"), obj])
     return exe
 
@@ -143,7 +143,7 @@ def test_parse_kernel_sources_build_the_true_index(oracle, tmp_path):
     exe = str(d / "run_parse_kernel")
     obj = str(d / "oracle.o")
     subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
                            "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_parse_kernel.cpp"), obj])
     rng = np.random.default_rng(9)
     raws = {n: read_data(n) for n in ("html", "alice29.txt", "fireworks.jpeg", "urls.10K", "sample-tweet.json", "kppkn.gtb")}
@@ -183,7 +183,7 @@ def test_page_kernel_sources_match_oracle_and_round_trip(tmp_path, rules):
     exe = str(tmp_path / "run_pages_kernel")
     obj = str(tmp_path / "oracle.o")
     subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
                            "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_pages_kernel.cpp"), obj])
     files = [os.path.join(DATA, f) for f in ("html", "alice29.txt", "fireworks.jpeg", "sample-tweet.json", "geo.protodata")]
     p = subprocess.run([exe] + files, env=dict(os.environ, RULES=str(rules)), capture_output=True, text=True)

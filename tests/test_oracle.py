@@ -184,3 +184,54 @@ def test_fragment_api_consistent(oracle):
     a, _ = oracle.compress_fragments(raw, len(raw), 0, 5)
     b, _ = oracle.compress_fragments(raw, len(raw), 5, nfrag - 5)
     assert hdr + a.tobytes() + b.tobytes() == whole
+
+
+# ---- the reference's literal lookup tables (src/internal.jl:47-85), extracted by tests/golden/make_char_table.py ----
+def _golden_char_table():
+    import json
+    import os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "char_table.json")) as f:
+        g = json.load(f)
+    assert len(g["char_table"]) == 256 and len(g["wordmask"]) == 5
+    return g
+
+
+def test_char_table_golden_matches_the_reference_source_when_present():
+    """in the build container the fixture is re-extracted from /root/reference and must equal the committed one"""
+    import os
+    import sys
+    from conftest import ROOT
+    if not os.path.exists("/root/reference/src/internal.jl"):
+        pytest.skip("reference sources are not on this box")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_char_table
+    g = _golden_char_table()
+    fresh = make_char_table.extract("/root/reference")
+    assert fresh["char_table"] == g["char_table"] and fresh["wordmask"] == g["wordmask"]
+
+
+def test_char_table_of_both_cpu_decoders_equals_the_reference_table(oracle):
+    """oracle/snappy_oracle.c and oracle/py_restatement.py regenerate CHAR_TABLE by formula: all 256 entries must be
+    the reference's literal ones"""
+    import py_restatement
+    g = _golden_char_table()
+    assert oracle.char_table() == g["char_table"]
+    assert [int(x) for x in py_restatement.CHAR_TABLE] == g["char_table"]
+
+
+def test_char_table_of_the_cuda_decoders_equals_the_reference_table(tmp_path):
+    """csrc/decompress.cuh evaluates CHAR_TABLE / WORDMASK arithmetically in decode_tag (exact decoder, parse
+    kernels) and decode_tag_fast (indexed decoder): the real header, compiled for the CPU, against the literal table"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "dump_char_table")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "dump_char_table.cpp")])
+    lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    g = _golden_char_table()
+    assert [int(x) for x in lines[0].split()] == g["char_table"]   # decode_tag
+    assert [int(x) for x in lines[1].split()] == g["char_table"]   # decode_tag_fast
+    assert [int(x) for x in lines[2].split()] == g["wordmask"]
+    assert [int(x) for x in lines[3].split()] == g["wordmask"]

@@ -119,3 +119,65 @@ def test_page_header_reader_rejects_malformed_input_quickly():
         with pytest.raises(ValueError):
             pp.read_page_header(blob, 0)
 
+
+
+# ---- hostile / malformed files: every length the kernel is handed is checked on the host first (no GPU needed)
+def _patched_headers(monkeypatch, pp, edit):
+    real = pp.read_page_header
+    state = {"n": 0}
+
+    def fake(buf, pos):
+        f, hl = real(buf, pos)
+        state["n"] += 1
+        edit(state["n"], f)
+        return f, hl
+
+    monkeypatch.setattr(pp, "read_page_header", fake)
+
+
+def test_page_body_past_the_file_image_is_rejected(monkeypatch):
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("1.0", 4096, rows=5_000)
+
+    def edit(n, fields):
+        if n == 3:
+            fields[3] = len(f)  # compressed_page_size larger than what is left of the file
+
+    _patched_headers(monkeypatch, pp, edit)
+    with pytest.raises(ValueError, match="past the end"):
+        pp.list_pages(f)
+
+
+def test_oversized_and_negative_page_sizes_are_rejected(monkeypatch):
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("2.0", 4096, rows=5_000)
+
+    def huge(n, fields):
+        if n == 2:
+            fields[3] = 1 << 31
+
+    _patched_headers(monkeypatch, pp, huge)
+    with pytest.raises(ValueError, match="2 GiB"):
+        pp.list_pages(f)
+
+    def levels(n, fields):
+        if fields[1] == pp.DATA_PAGE_V2:
+            fields[8][5] = fields[3] + 1  # more level bytes than the page holds: usize - prefix would go negative
+
+    _patched_headers(monkeypatch, pp, levels)
+    with pytest.raises(ValueError, match="level bytes"):
+        pp.list_pages(f)
+
+
+def test_caller_supplied_page_list_is_checked():
+    from snappy_jl_b200 import parquet_pages as pp
+    f = make_file("1.0", 4096, rows=5_000)
+    pages = pp.list_pages(f)
+    k = next(i for i, p in enumerate(pages) if p["codec"] == "SNAPPY" and p["compressed"] > 0)
+    bad = [dict(p) for p in pages]
+    bad[k]["compressed"] = len(f)  # would make k_decode_pages read past d_file
+    with pytest.raises(ValueError, match="does not fit"):
+        pp.uncompress_pages(f, bad)
+    truncated = f[: pages[k]["stream"] + 3]
+    with pytest.raises(ValueError, match="does not fit"):
+        pp.uncompress_pages(truncated, pages)

@@ -72,7 +72,7 @@ def main():
     exe = {}
     for name in ("window", "decode", "pages", "parse"):
         exe[name] = os.path.join(d, name)
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"), "-o",
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"), "-o",
                                exe[name], os.path.join(ROOT, "tools", "cpu_warp", "run_%s_kernel.cpp" % name), obj])
     raw, streams = [], []
     codec = pa.Codec("snappy")
