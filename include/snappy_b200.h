@@ -138,6 +138,49 @@ int snappy_b200_uncompress_shards_device(const uint8_t *const *d_ins,
                                          const size_t *out_lens, size_t count,
                                          uint8_t *const *d_outs, void *stream);
 
+/* ---- multi-GPU communicator: the sharded path with its exchange steps inside the library -------------------
+ * (replaces the implicit contiguous write of src/Snappy.jl:25-35 across GPUs.)
+ * One process per GPU.  Stream s of a call is OWNED by rank s mod world; rank r holds, of every stream, the run of
+ * whole 64 KiB fragments that whole-fragment sharding gives it: with nfrag = ceil(total/65536), the first
+ * nfrag mod world ranks hold nfrag/world + 1 fragments, the others nfrag/world, in rank order.
+ * Exchange steps, all on the caller's stream: ncclAllGather of the compressed byte counts, then every fragment is
+ * stored straight into the owner's buffer through a peer-mapped pointer (cudaIpc, NVLink), side-index entries
+ * included; uncompress loads each rank's compressed range from the owner the same way.  NCCL is bound at run time
+ * (the copy already loaded in the process, else libnccl.so.2). */
+typedef struct snappy_b200_comm snappy_b200_comm;
+
+/* Rank 0 makes the 128-byte id (ncclGetUniqueId); the host's own plumbing (torch.distributed, MPI.jl, a file)
+ * carries it to the other ranks. */
+int snappy_b200_comm_unique_id(uint8_t id[128]);
+/* Collective over `world` processes, each on its own GPU (the calling thread's device).  world == 1 needs no id. */
+int snappy_b200_comm_create(const uint8_t id[128], int rank, int world, snappy_b200_comm **out);
+/* A world whose `world` ranks all live in this process on the current device: no NCCL, no IPC; per-rank argument
+ * arrays then carry world x nstreams entries, rank-major.  What a single GPU uses to push many streams through one
+ * kernel pass (world = 1), and what lets one GPU run the exact multi-rank data path (tests). */
+int snappy_b200_comm_create_loopback(int world, snappy_b200_comm **out);
+void snappy_b200_comm_destroy(snappy_b200_comm *comm);
+int snappy_b200_comm_info(const snappy_b200_comm *comm, int *world, int *nlocal, int *rank0);
+
+/* Collective.  d_shards / shard_lens: nlocal x nstreams entries (rank-major): the local ranks' runs of every stream
+ * (device pointers; NULL / 0 where a rank's run is empty).  total_lens[nstreams]: the same on every rank.
+ * For every stream owned by a local rank: out_streams[s] = device pointer to the assembled stream (header +
+ * elements), out_index[s] = its side index (nfrag + 1 offsets); both point into the communicator's arena and stay
+ * valid until the next call on it.  out_lens[s] is set for EVERY stream.  Other entries are NULL.
+ * Bytes are identical to snappy_b200_compress_device on the whole stream.  Synchronises `stream`. */
+int snappy_b200_comm_compress(snappy_b200_comm *comm, const uint8_t *const *d_shards, const size_t *shard_lens,
+                              const uint64_t *total_lens, size_t nstreams, uint8_t **out_streams, size_t *out_lens,
+                              uint64_t **out_index, void *stream);
+
+/* Collective inverse.  For streams owned by a local rank: d_streams[s] / stream_lens[s] (any device memory, or the
+ * pointers comm_compress returned) and optionally d_index[s] (NULL, or d_index == NULL: the owner parses its stream).
+ * d_outs: nlocal x nstreams device pointers; each receives that rank's run of the stream (the output stays
+ * sharded).  statuses (optional, nstreams): the reference's status per stream, agreed by all ranks
+ * (src/internal.jl:499,505,518, src/Snappy.jl:50); BAD_ARGUMENT marks a valid stream that cannot be decoded in
+ * shards (elements straddling 64 KiB output boundaries): decode it on one GPU.  Returns the first non-OK status. */
+int snappy_b200_comm_uncompress(snappy_b200_comm *comm, const uint8_t *const *d_streams, const size_t *stream_lens,
+                                const uint64_t *const *d_index, const uint64_t *total_lens, size_t nstreams,
+                                uint8_t *const *d_outs, int *statuses, void *stream);
+
 /* varint.jl:46-69 / :12-37 on the host (the stream header). Returns bytes written (1..5). */
 int snappy_b200_encode_header(uint32_t value, uint8_t out[5]);
 int snappy_b200_parse_header(const uint8_t *in, size_t n, uint32_t *value, size_t *header_len);

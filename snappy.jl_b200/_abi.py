@@ -48,6 +48,14 @@ SIGNATURES = {
     "snappy_b200_uncompress_shard_device": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "snappy_b200_compress_shards_device": (ctypes.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "snappy_b200_uncompress_shards_device": (ctypes.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "snappy_b200_comm_unique_id": (ctypes.c_int, [_vp]),
+    "snappy_b200_comm_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "snappy_b200_comm_create_loopback": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "snappy_b200_comm_destroy": (None, [_vp]),
+    "snappy_b200_comm_info": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_int)]),
+    "snappy_b200_comm_compress": (ctypes.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "snappy_b200_comm_uncompress": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "snappy_b200_encode_header": (ctypes.c_int, [ctypes.c_uint32, _vp]),
     "snappy_b200_parse_header": (ctypes.c_int, [_vp, _sz, ctypes.POINTER(ctypes.c_uint32), _szp]),
     "snappy_b200_find_match_length": (_sz, [_vp, _sz, _sz, _sz]),

@@ -61,6 +61,15 @@ __global__ void k_init_probe_offsets() {
 // kLib: libsnappy emission rules instead of Snappy.jl's (option `rules`): ip_limit =
 // n - 15, a 60-byte literal keeps the one-byte header, the table is sized per fragment and the bucket of a hash
 // is ((w * mul) >> shift) & hmask (rules = 2: Google snappy >= 1.1.9, shift 17 and up to 32768 buckets).
+// Output bytes of a fragment are written once and read once, much later, by the compaction kernel: with
+// SB200_OUT_CS they are stored with the streaming (evict-first) policy, so that they do not push the fragment bytes
+// the global-table warps gather their far candidates from out of L2.
+#if defined(SB200_OUT_CS) && !defined(SB200_CPU_EMU)
+#define SB200_ST8(p, v) __stcs((p), (u8)(v))
+#else
+#define SB200_ST8(p, v) (*(p) = (u8)(v))
+#endif
+
 template <bool kSmemTable, bool kLib = false>
 struct Chain {
     static constexpr u32 kLitShort = kLib ? 61u : 60u;   // literals below this take the one-byte header (:271)
@@ -123,14 +132,14 @@ struct Chain {
     }
     static __device__ __forceinline__ u32 put_op(u8* o, u32 p, u32 off, u32 len) {  // :289-304
         if (len < 12 && off < 2048) {
-            o[p] = (u8)(1 + ((len - 4) << 2) + ((off >> 3) & 0xe0));
-            o[p + 1] = (u8)off;
+            SB200_ST8(o + p, 1 + ((len - 4) << 2) + ((off >> 3) & 0xe0));
+            SB200_ST8(o + p + 1, off);
             return p + 2;
         }
         const u32 u = 2 + ((len - 1) << 2) + (off << 8);
-        o[p] = (u8)u;
-        o[p + 1] = (u8)(u >> 8);
-        o[p + 2] = (u8)(u >> 16);
+        SB200_ST8(o + p, u);
+        SB200_ST8(o + p + 1, u >> 8);
+        SB200_ST8(o + p + 2, u >> 16);
         return p + 3;
     }
 
@@ -164,12 +173,12 @@ struct Chain {
         if (ll) {
             const u32 nm1 = ll - 1;
             if (ll < kLitShort) {
-                out[pos] = (u8)(nm1 << 2);
+                SB200_ST8(out + pos, nm1 << 2);
             } else {
-                out[pos] = (u8)((59 + (lh - 1)) << 2);
-                out[pos + 1] = (u8)nm1;
-                if (lh > 2) out[pos + 2] = (u8)(nm1 >> 8);
-                if (lh > 3) out[pos + 3] = (u8)(nm1 >> 16);
+                SB200_ST8(out + pos, (59 + (lh - 1)) << 2);
+                SB200_ST8(out + pos + 1, nm1);
+                if (lh > 2) SB200_ST8(out + pos + 2, nm1 >> 8);
+                if (lh > 3) SB200_ST8(out + pos + 3, nm1 >> 16);
             }
             if (ll <= 16) {
                 // <= 16 literal bytes through the aligned words that hold them (only words with a wanted byte are
@@ -186,7 +195,7 @@ struct Chain {
 #pragma unroll
                 for (u32 i = 0; i < 16; i++) {
                     const u32 word = i < 4 ? b0 : (i < 8 ? b1 : (i < 12 ? b2 : b3));
-                    if (i < ll) d[i] = (u8)(word >> (8 * (i & 3)));
+                    if (i < ll) SB200_ST8(d + i, word >> (8 * (i & 3)));
                 }
             }
         }
@@ -197,7 +206,7 @@ struct Chain {
             const u32 src = __shfl_sync(kFullMask, lf, j);
             const u32 len = __shfl_sync(kFullMask, ll, j);
             const u32 dst = __shfl_sync(kFullMask, pos + lh, j);
-            for (u32 k = lane; k < len; k += 32) out[dst + k] = __ldg(F + src + k);
+            for (u32 k = lane; k < len; k += 32) SB200_ST8(out + dst + k, __ldg(F + src + k));
         }
         if (M) {  // :306-329
             u32 p = pos + lh + ll, len = M;

@@ -327,6 +327,7 @@ struct DecodeDesc {
     u8* out;
     u64 out_len;
     u32 frag_begin, nfrag;
+    u32* flag;   // optional: raised when a fragment of THIS shard is not clean (besides res->fallback)
 };
 
 template <int kMinBlocks>
@@ -341,9 +342,11 @@ k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, 
     const u32 local = blockIdx.x * kDecodeWarpsPerCta + (threadIdx.x >> 5);
     if (local >= count) return;
     u32 f = first + local;
+    u32* shard_flag = nullptr;
     if (descs) {  // batched shards: find the shard, take its own arrays and bounds
         u32 k = 0;
         while (k + 1 < ndesc && descs[k + 1].frag_begin <= f) k++;
+        shard_flag = descs[k].flag;
         in = descs[k].in;
         frag_off = descs[k].frag_off;
         out = descs[k].out;
@@ -360,7 +363,10 @@ k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, 
     bool ok = (ie >= ip) && (ie <= in_end) && (f != 0 || ip == in_begin) &&
               (f != nfrag - 1 || ie == in_end);
     if (ok) ok = decode_fast_warp(in, ip, ie, out + ob, on, lane);
-    if (!ok && lane == 0) atomicOr(&res->fallback, 1u);
+    if (!ok && lane == 0) {
+        atomicOr(&res->fallback, 1u);
+        if (shard_flag) atomicOr(shard_flag, 1u);
+    }
 }
 
 // Batched pages: one warp per independent stream (own varint header).  Fast path first; the exact

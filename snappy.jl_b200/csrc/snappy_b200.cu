@@ -5,6 +5,7 @@
 // the codec itself runs only as sm_100a kernels (compress.cuh / decompress.cuh).  No CPU fallback.
 #include "../../include/snappy_b200.h"
 
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -83,6 +84,7 @@ struct Options {
     int uncompress_segments = 8;  // streamed host-buffer uncompress: segments the stream is parsed in (2, 4 or 8)
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
+    int profile_range = 0;      // 1 = cudaProfilerStart/Stop around the concurrent compress kernels (ncu --replay-mode range)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
     int pin_host = 1;           // host-buffer API on pageable memory: register the caller's buffers for the call
 };
@@ -189,6 +191,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "decode_occupancy")) g_opt.decode_occupancy = value;
     else if (!strcmp(name, "timing")) g_opt.timing = value;
     else if (!strcmp(name, "lpt")) g_opt.lpt = value;
+    else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
 }
 
@@ -448,6 +451,12 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         if (rc != SNAPPY_B200_OK) return rc;
     }
     u32* counter = (u32*)((u8*)c.result.p + 64);
+    // profile_range: the two concurrent kernels (and the counter reset they depend on) form one ncu range
+    const bool prof = c.opt.profile_range != 0;
+    if (prof) {
+        CU(cudaStreamSynchronize(st));
+        cudaProfilerStart();
+    }
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // fragment order: expensive first (schedule.cuh).  Not for the streamed host path (fragments become resident
     // in stream order) and pointless below a few fragments per warp.
@@ -560,6 +569,10 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
+    }
+    if (prof) {
+        CU(cudaStreamSynchronize(st));
+        cudaProfilerStop();
     }
     return SNAPPY_B200_OK;
 }
@@ -1053,6 +1066,7 @@ size_t snappy_b200_find_match_length(const uint8_t* a, size_t i1, size_t i2, siz
 int snappy_b200_compress_device(const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap,
                                 size_t* out_len, uint64_t* d_frag_index, void* stream) {
     if (!out_len || (!d_in && n) || !d_out) return SNAPPY_B200_BAD_ARGUMENT;
+    if (n > 0xffffffffull) return SNAPPY_B200_INPUT_TOO_LARGE;  // src/Snappy.jl:21 (before any device work)
     Locked L;
     if (L.rc != SNAPPY_B200_OK) return L.rc;
     return compress_device_locked(*L.c, d_in, n, d_out, out_cap, out_len, (u64*)d_frag_index,
@@ -1539,6 +1553,7 @@ int snappy_b200_uncompress_shards_device(const uint8_t* const* d_ins, const uint
         d.out_len = out_lens[k];
         d.frag_begin = (u32)nfrag_total;
         d.nfrag = nf;
+        d.flag = nullptr;
         descs.push_back(d);
         nfrag_total += nf;
     }
@@ -1768,3 +1783,6 @@ void snappy_b200_set_option(const char* name, int value) {
 }
 
 }  // extern "C"
+
+// ---- multi-GPU communicator ----------------------------------------------------------
+#include "multi_host.inc"

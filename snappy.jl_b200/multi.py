@@ -194,3 +194,135 @@ def uncompress_streams(stream, index, total_len, codec, group=None):
     if hasattr(codec, "uncompress_shards"):
         return codec.uncompress_shards(datas, fos, out_lens)
     return [codec.uncompress_shard(datas[s], fos[s].contiguous(), out_lens[s]) for s in range(world)]
+
+
+# ------------------------------------------------------------------------------------------------------
+# Library path (CUDA): the exchange steps live in libsnappy_b200.so (csrc/multi_host.inc, csrc/multi.cuh):
+# ncclAllGather of the byte counts on the compute stream, fragments and side-index entries stored straight into
+# the owner's buffer through cudaIpc-mapped peer pointers (NVLink), the inverse by peer loads.  torch.distributed
+# only carries the 128-byte NCCL id to the other ranks.  The functions above remain the host-logic reference that
+# the gloo tests run on CPU tensors.
+# ------------------------------------------------------------------------------------------------------
+import ctypes
+
+
+class _DevMem:
+    """A device pointer + length as a __cuda_array_interface__ object (zero-copy torch view of arena memory)."""
+
+    def __init__(self, ptr, nbytes, typestr="|u1", itemsize=1):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def _view_u8(ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevMem(ptr, n), device=device)
+
+
+def _view_i64(ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevMem(ptr, n * 8, "<i8", 8), device=device)
+
+
+class LibComm:
+    """snappy_b200_comm: `world` ranks, `nlocal` of them hosted by this process (1 under torchrun; all of them in a
+    loopback world on one GPU).  Stream s is owned by rank s % world.
+
+    compress(shards, total_lens) / uncompress(streams, indexes, total_lens) are collective; the per-rank argument
+    lists are rank-major over the local ranks: entry [lr * nstreams + s]."""
+
+    def __init__(self, group=None, loopback_world=None, device=None):
+        from . import _abi
+        from .api import _check
+        self._abi, self._check = _abi, _check
+        self.handle = ctypes.c_void_p(0)
+        if loopback_world is not None:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+            with torch.cuda.device(self.device):
+                _check(_abi.lib().snappy_b200_comm_create_loopback(int(loopback_world), ctypes.byref(self.handle)))
+            self.world, self.nlocal, self.rank0 = int(loopback_world), int(loopback_world), 0
+            return
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        ident = (ctypes.c_uint8 * 128)()
+        if world > 1:
+            t = torch.zeros(128, dtype=torch.uint8, device=self.device)
+            if rank == 0:
+                _check(_abi.lib().snappy_b200_comm_unique_id(ident))
+                t.copy_(torch.frombuffer(bytearray(bytes(ident)), dtype=torch.uint8))
+            dist.broadcast(t, src=0, group=group)  # plumbing: the id is all torch.distributed carries
+            raw = bytes(t.cpu().numpy().tobytes())
+            ident = (ctypes.c_uint8 * 128).from_buffer_copy(raw)
+        with torch.cuda.device(self.device):
+            _check(_abi.lib().snappy_b200_comm_create(ident, rank, world, ctypes.byref(self.handle)))
+        self.world, self.nlocal, self.rank0 = world, 1, rank
+
+    def close(self):
+        if self.handle:
+            self._abi.lib().snappy_b200_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def owns(self, s):
+        return self.rank0 <= s % self.world < self.rank0 + self.nlocal
+
+    def compress(self, shards, total_lens):
+        """shards: nlocal * nstreams uint8 CUDA tensors (or None for an empty run).  Returns (streams, indexes,
+        lens): per stream a zero-copy view of the assembled stream and of its side index (None for streams owned
+        elsewhere) and the stream length (known everywhere).  Views stay valid until the next compress()."""
+        S = len(total_lens)
+        assert len(shards) == self.nlocal * S
+        n = len(shards)
+        ptrs = (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None and t.numel() else 0) for t in shards])
+        lens = (ctypes.c_size_t * n)(*[(t.numel() if t is not None else 0) for t in shards])
+        totals = (ctypes.c_uint64 * S)(*[int(x) for x in total_lens])
+        o_streams = (ctypes.c_void_p * S)()
+        o_lens = (ctypes.c_size_t * S)()
+        o_index = (ctypes.c_void_p * S)()
+        with torch.cuda.device(self.device):
+            self._check(self._abi.lib().snappy_b200_comm_compress(
+                self.handle, ptrs, lens, totals, S, o_streams, o_lens, o_index,
+                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        streams, indexes = [], []
+        for s in range(S):
+            if o_streams[s]:
+                nfrag = (int(total_lens[s]) + FRAGMENT - 1) // FRAGMENT
+                streams.append(_view_u8(o_streams[s], int(o_lens[s]), self.device))
+                indexes.append(_view_i64(o_index[s], nfrag + 1, self.device))
+            else:
+                streams.append(None)
+                indexes.append(None)
+        return streams, indexes, [int(x) for x in o_lens]
+
+    def uncompress(self, streams, indexes, total_lens, outs=None, statuses_out=None):
+        """streams / indexes: per stream, given where a local rank owns it (None elsewhere; index may be None:
+        the owner parses).  Returns the local ranks' decoded runs, nlocal * nstreams tensors (rank-major)."""
+        S = len(total_lens)
+        sp = (ctypes.c_void_p * S)(*[(t.data_ptr() if t is not None and t.numel() else 0) for t in streams])
+        sl = (ctypes.c_size_t * S)(*[(t.numel() if t is not None else 0) for t in streams])
+        ip = (ctypes.c_void_p * S)(*[(t.data_ptr() if t is not None and t.numel() else 0) for t in indexes])
+        totals = (ctypes.c_uint64 * S)(*[int(x) for x in total_lens])
+        if outs is None:
+            outs = []
+            for lr in range(self.nlocal):
+                for s in range(S):
+                    lo, hi = shard_bounds(int(total_lens[s]), self.world)[self.rank0 + lr]
+                    outs.append(torch.empty(hi - lo, dtype=torch.uint8, device=self.device))
+        op = (ctypes.c_void_p * len(outs))(*[(t.data_ptr() if t.numel() else 0) for t in outs])
+        st = (ctypes.c_int * S)()
+        with torch.cuda.device(self.device):
+            rc = self._abi.lib().snappy_b200_comm_uncompress(
+                self.handle, sp, sl, ip, totals, S, op, st,
+                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if statuses_out is not None:
+            statuses_out[:] = [int(x) for x in st]
+        self._check(rc)
+        return outs

@@ -161,3 +161,31 @@ def test_index_sidecar_fuzz_with_valid_checksum(snappy):
         assert np.all(np.diff(back.astype(np.int64)) >= 0) or int(back[-1]) < 2 ** 63
         assert snappy.unpack_index(snappy.pack_index(back, ulen))[1:] == (ulen, slen)
     assert rejected > 1000 and accepted + rejected == 3000
+
+
+def test_input_too_large_at_2_pow_32(snappy):
+    """src/Snappy.jl:21: `length(input) > 2^32 - 1` is "Input too large." -- decided from the length alone, before any
+    byte is read or any device is touched (so the check needs neither 4 GiB of memory nor a GPU)."""
+    import ctypes
+    lib = snappy._abi.lib()
+    buf = (ctypes.c_uint8 * 16)()
+    out_len = ctypes.c_size_t(1 << 40)
+    for n in (1 << 32, (1 << 32) + 1, 1 << 40):
+        assert lib.snappy_b200_compress(buf, n, buf, ctypes.byref(out_len)) == snappy._abi.INPUT_TOO_LARGE
+        assert lib.snappy_b200_compress_device(buf, n, buf, 1 << 41, ctypes.byref(out_len), None, None) == \
+            snappy._abi.INPUT_TOO_LARGE
+        assert lib.snappy_b200_compress_shard_device(buf, 65536, n, buf, 1 << 20, ctypes.byref(out_len), None,
+                                                     None) == snappy._abi.INPUT_TOO_LARGE
+    assert snappy._abi.status_string(snappy._abi.INPUT_TOO_LARGE) == "Input too large."
+    # the largest legal length passes the length check (and then stops at the next one: the output capacity)
+    small = ctypes.c_size_t(16)
+    assert lib.snappy_b200_compress(buf, (1 << 32) - 1, buf, ctypes.byref(small)) == snappy._abi.BUFFER_TOO_SMALL
+
+
+def test_get_option_and_product_build_has_no_experiments(snappy):
+    lib = snappy._abi.lib()
+    assert lib.snappy_b200_get_option(b"experiments") == 0  # the shipped library holds the default kernels only
+    assert lib.snappy_b200_get_option(b"rules") == 0 and lib.snappy_b200_get_option(b"lpt") == 1
+    assert lib.snappy_b200_get_option(b"no_such_option") == -1
+    lib.snappy_b200_set_option(b"wide", 4)  # experiment selectors are inert in the product build
+    assert lib.snappy_b200_get_option(b"wide") == 0
