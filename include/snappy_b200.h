@@ -226,6 +226,11 @@ void snappy_b200_set_option(const char *name, int value);
 /* Current value of an option, or -1 for a name this build does not know.  "experiments" reads 1 in a build that
  * also holds the measured-and-rejected kernel designs (make -C snappy.jl_b200/csrc exp), 0 in the product build. */
 int snappy_b200_get_option(const char *name);
+/* With option "trace" = 1 the compress warps record when they began and finished every fragment (globaltimer ns;
+ * begin carries the table placement in bit 0, end the SM number in its low 8 bits): 2 x uint64 per fragment of the
+ * calling thread's last compress call.  Returns the fragments copied.  tools/trace_frags.py turns it into the
+ * utilisation timeline and the length of the launch's tail. */
+size_t snappy_b200_debug_trace(uint64_t *out, size_t max_frags);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,8 @@ def lib():
         L.sjo_compress_fragments.restype = ctypes.c_size_t
         L.sjo_compress_fragments.argtypes = [u8p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t,
                                              u8p, ctypes.c_void_p]
+        L.sjo_compress_fragment.restype = ctypes.c_size_t
+        L.sjo_compress_fragment.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_void_p, ctypes.c_uint32]
         L.sjo_compress.restype = ctypes.c_int
         L.sjo_compress.argtypes = [u8p, ctypes.c_size_t, u8p, szp]
         L.sjo_compress_rules.restype = ctypes.c_int
@@ -127,6 +129,18 @@ def compress_fragments(data, total_len, first_frag, nfrag):
     n = lib().sjo_compress_fragments(_ptr(a), total_len, first_frag, nfrag, _ptr(out),
                                      ctypes.c_void_p(sizes.ctypes.data))
     return out[:n], sizes[:nfrag]
+
+
+def compress_one_fragment(frag, total_len):
+    """One <= 64 KiB fragment of a stream whose TOTAL length is total_len (the table is sized from the total,
+    Snappy.jl:27, and reset per fragment, :30): the fragment's element bytes, no header."""
+    a = _as_u8(frag)
+    assert a.size <= 65536
+    entries = lib().sjo_hashtable_entries(int(total_len))
+    table = np.full(16384, 0xFFFF, dtype=np.uint16)
+    out = np.empty(65536 + 65536 // 6 + 64, dtype=np.uint8)
+    n = lib().sjo_compress_fragment(_ptr(a), a.size, _ptr(out), ctypes.c_void_p(table.ctypes.data), entries)
+    return out[:n]
 
 
 def uncompressed_length(data):

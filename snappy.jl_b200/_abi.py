@@ -63,6 +63,7 @@ SIGNATURES = {
     "snappy_b200_last_launch_count": (ctypes.c_int, [ctypes.c_int]),
     "snappy_b200_set_option": (None, [ctypes.c_char_p, ctypes.c_int]),
     "snappy_b200_get_option": (ctypes.c_int, [ctypes.c_char_p]),
+    "snappy_b200_debug_trace": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_size_t]),
     "snappy_b200_index_pack_bound": (ctypes.c_size_t, [ctypes.c_size_t]),
     "snappy_b200_index_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p,
                                               ctypes.POINTER(ctypes.c_size_t)]),

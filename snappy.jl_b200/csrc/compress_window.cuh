@@ -426,7 +426,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
                   u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
                   const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes,
                   const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1, u32 lib_rules = 0,
-                  const u32* __restrict__ order = nullptr) {
+                  const u32* __restrict__ order = nullptr, u64* __restrict__ trace = nullptr) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarp = blockDim.x >> 5;
@@ -442,6 +442,8 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         frag = __shfl_sync(kFullMask, frag, 0);
         if (frag >= nfrag) break;
         if (order) frag = order[frag];  // schedule.cuh: expensive fragments first (never together with `ready`)
+        u64 t_begin = 0;
+        if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
         if (ready) {  // streamed input (host-buffer API): wait until this fragment and the one behind it
                       // (the kernel reads a few bytes past a fragment's end) have landed
             if (lane == 0) {
@@ -493,6 +495,14 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
         ch.run_window();
         if (lane == 0) frag_sizes[frag] = ch.op;
+        if (trace && lane == 0) {  // option `trace`: [begin ns | table placement in bit 0, end ns | SM in the low 8 bits]
+            u64 t_end;
+            u32 smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace[2 * (u64)frag] = (t_begin & ~(u64)1) | (kSmemTable ? 1u : 0u);
+            trace[2 * (u64)frag + 1] = (t_end & ~(u64)0xff) | (smid & 0xffu);
+        }
         if (done) {  // streamed output: per-chunk completion counts release the compaction of a chunk
             __threadfence();
             __syncwarp();

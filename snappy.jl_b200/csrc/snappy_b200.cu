@@ -84,6 +84,7 @@ struct Options {
     int uncompress_segments = 8;  // streamed host-buffer uncompress: segments the stream is parsed in (2, 4 or 8)
     int host_pipeline = 1;      // host-buffer API: overlap H2D / kernels / D2H in chunks
     int timing = 1;             // record CUDA events around the dominant kernel
+    int trace = 0;              // 1 = the compress warps record begin / end time of every fragment (snappy_b200_debug_trace)
     int profile_range = 0;      // 1 = cudaProfilerStart/Stop around the concurrent compress kernels (ncu --replay-mode range)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
     int pin_host = 1;           // host-buffer API on pageable memory: register the caller's buffers for the call
@@ -100,7 +101,8 @@ struct Context {
     int sm_count = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
     // scratch for compress
-    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags, order;
+    DevBuf scratch, frag_sizes, frag_offsets, tail, gtables, descs, flags, order, trace;
+    u32 trace_frags = 0;
     cudaStream_t side = nullptr;      // second stream for the global-table warps
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr, s_pack = nullptr;  // host-buffer API pipeline
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
@@ -192,6 +194,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "timing")) g_opt.timing = value;
     else if (!strcmp(name, "lpt")) g_opt.lpt = value;
     else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
+    else if (!strcmp(name, "trace")) g_opt.trace = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
 }
 
@@ -357,7 +360,7 @@ void ctx_destroy(Context& c) {
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
     for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a,
-                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order})
+                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order, &c.trace})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
     if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
@@ -460,6 +463,13 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     CU(cudaMemsetAsync(counter, 0, 4, st));
     // fragment order: expensive first (schedule.cuh).  Not for the streamed host path (fragments become resident
     // in stream order) and pointless below a few fragments per warp.
+    u64* trace = nullptr;
+    if (c.opt.trace) {
+        CU(c.trace.ensure((size_t)nfrag * 16));
+        CU(cudaMemsetAsync(c.trace.p, 0, (size_t)nfrag * 16, st));
+        trace = (u64*)c.trace.p;
+        c.trace_frags = nfrag;
+    }
     const u32* order = nullptr;
     if (c.opt.lpt && !gate && nfrag >= 2u * (u32)c.sm_count) {
         CU(c.order.ensure((size_t)nfrag * 5));
@@ -512,7 +522,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         if (rules)
             k_compress_window<true, true><<<ctas_a, wa * 32, (size_t)wa * (tab_bytes + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules, order);
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules, order, trace);
 #ifdef SB200_EXPERIMENTS
         else if (window && c.opt.slowcont)
             k_compress_window<true, false, true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
@@ -526,7 +536,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         else
             k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, 0u, order);
+                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, 0u, order, trace);
     }
     *launches += 1;
     if (ctas_b) {
@@ -549,7 +559,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             k_compress_window<false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u, rules, order);
+                gate ? gate->div : 1u, rules, order, trace);
 #ifdef SB200_EXPERIMENTS
         else if (window && c.opt.slowcont)
             k_compress_window<false, false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
@@ -565,7 +575,7 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
                 reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u, 0u, order);
+                gate ? gate->div : 1u, 0u, order, trace);
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -1749,6 +1759,21 @@ int snappy_b200_last_launch_count(int which) {
 }
 
 
+// option `trace`: begin / end of every fragment of this thread's last compress call (2 x u64 per fragment, see
+// k_compress_window); returns the number of fragments copied
+size_t snappy_b200_debug_trace(uint64_t* out, size_t max_frags) {
+    Context* c = tl_last;
+    if (!c || !out || !c->trace.p) return 0;
+    std::unique_lock<std::mutex> lk(c->mu);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    const size_t n = c->trace_frags < max_frags ? c->trace_frags : max_frags;
+    cudaMemcpy(out, c->trace.p, n * 16, cudaMemcpyDeviceToHost);
+    if (prev >= 0) cudaSetDevice(prev);
+    return n;
+}
+
 int snappy_b200_get_option(const char* name) {
     if (!name) return -1;
     parse_env_options();
@@ -1769,7 +1794,8 @@ int snappy_b200_get_option(const char* name) {
         {"parse_chunk_log2", o.parse_chunk_log2}, {"uncompress_segments", o.uncompress_segments},
         {"host_pipeline", o.host_pipeline}, {"timing", o.timing}, {"l2_persist", o.l2_persist},
         {"overlap_compact", o.overlap_compact}, {"window", o.window}, {"wide", o.wide}, {"slowcont", o.slowcont},
-        {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host},
+        {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host}, {"trace", o.trace},
+        {"profile_range", o.profile_range},
     };
     for (const auto& e : tab)
         if (!strcmp(name, e.n)) return e.v;

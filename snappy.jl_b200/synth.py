@@ -184,3 +184,69 @@ def pages(count, page_size=4096, seed=2026):
     per_frag = FRAGMENT // page_size
     nfrag = (count + per_frag - 1) // per_frag
     return mix(nfrag, seed)[: count * page_size].reshape(count, page_size)
+
+
+# ---- several buffers at once: worker processes fill one shared-memory segment (bench.py: 1 GiB of mix takes ~26 s
+# and 1 GiB of source-like text ~43 s on one core) -----------------------------------------------------------------
+def _gen_piece(job):
+    """worker process: one piece straight into the shared file mapping"""
+    kind, seed, nfrag, path, offset = job
+    a = source_like(nfrag * FRAGMENT, seed=seed) if kind == "source" else mix(nfrag, seed=seed)
+    m = np.memmap(path, dtype=np.uint8, mode="r+", offset=offset, shape=(a.size,))
+    m[:] = a
+    m.flush()
+    del m
+    return a.size
+
+
+class ParallelGenerator:
+    """add(kind, seed, nfrag) -> (offset, nbytes) of a piece (kind "source": source_like, anything else: mix);
+    run() generates all pieces side by side in spawned workers (no CUDA state is forked) into one file mapping
+    (/dev/shm when it has the room, else the temp directory); view() reads them."""
+
+    def __init__(self, workers):
+        self.jobs, self.total, self.workers = [], 0, max(1, int(workers))
+        self.path, self.map = None, None
+
+    def add(self, kind, seed, nfrag):
+        off = self.total
+        self.jobs.append([kind, int(seed), int(nfrag), None, off])
+        self.total += nfrag * FRAGMENT
+        return off, nfrag * FRAGMENT
+
+    def run(self):
+        import os
+        import shutil
+        import tempfile
+        from concurrent.futures import ProcessPoolExecutor
+        from multiprocessing import get_context
+        if not self.jobs:
+            return
+        where = None
+        try:
+            if shutil.disk_usage("/dev/shm").free > self.total + (1 << 30):
+                where = "/dev/shm"
+        except Exception:
+            pass
+        fd, self.path = tempfile.mkstemp(prefix="sb200_gen_", dir=where)
+        os.ftruncate(fd, max(self.total, 1))
+        os.close(fd)
+        for j in self.jobs:
+            j[3] = self.path
+        order = sorted(self.jobs, key=lambda j: -j[2])  # longest first; the pieces are independent
+        with ProcessPoolExecutor(max_workers=min(self.workers, len(order)), mp_context=get_context("spawn")) as ex:
+            list(ex.map(_gen_piece, [tuple(j) for j in order]))
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r", shape=(max(self.total, 1),))
+
+    def view(self, off, nbytes):
+        return self.map[off: off + nbytes]
+
+    def close(self):
+        import os
+        self.map = None
+        if self.path is not None:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+            self.path = None
