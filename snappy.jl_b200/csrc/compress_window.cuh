@@ -414,57 +414,67 @@ struct Win : Chain<kSmemTable, kLib> {
     }
 };
 
-// Persistent warps, as k_compress_chain; each warp additionally owns `ring_bytes` of shared memory
-// (behind the tables for the shared-table variant).
-// order (optional): the k-th fragment pulled is order[k] (schedule.cuh); the bytes do not depend on it.
-// kLib (option `rules`): libsnappy's rules; lib_rules = 1: libsnappy <= 1.1.7 (hash >> shift, <= 16384 buckets),
-// 2: Google snappy >= 1.1.9 ((hash >> 17) & mask, <= 32768 buckets: 64 KiB tables); table size per fragment.
-template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
-__global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
-k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift,
-                  const u8* __restrict__ tail_copy, u8* __restrict__ scratch, u32* __restrict__ frag_sizes,
-                  u32* __restrict__ counter, u16* __restrict__ gtables, u32 reserve,
-                  const ShardDesc* __restrict__ descs, u32 ndesc, u32 ring_bytes,
-                  const u32* ready = nullptr, u32* done = nullptr, u32 done_div = 1, u32 lib_rules = 0,
-                  const u32* __restrict__ order = nullptr, u64* __restrict__ trace = nullptr) {
-    extern __shared__ __align__(128) u8 smem[];
-    const u32 warp = threadIdx.x >> 5;
-    const u32 nwarp = blockDim.x >> 5;
-    const u32 gwarp = blockIdx.x * nwarp + warp;
-    const u32 tab = kLib ? (lib_rules == 2u ? 2u * kMaxTableEntries : kMaxTableEntries) : kMaxTableEntries;
-    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * tab : gtables + (size_t)gwarp * tab;
-    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * tab * 2u : 0u) + warp * (ring_bytes + kRingMirror);
+// Arguments of a window-kernel launch (one struct: the two kernel forms below share them).
+struct WindowArgs {
+    const u8* g_in;        // the shard (nullptr with descs)
+    u64 shard_len;
+    u32 nfrag, shift;
+    const u8* tail_copy;   // padded copy of the shard's last fragment (reads may run past a fragment's end)
+    u8* scratch;           // per-fragment output slots of kSlotStride bytes
+    u32* frag_sizes;
+    u32* counter;          // fragments are pulled from here
+    u16* gtables;          // one table per global-table warp
+    u32 reserve;           // global-table warps stop pulling when fewer than this many fragments remain
+    const ShardDesc* descs;
+    u32 ndesc;
+    const u32* ready;      // streamed input (host-buffer API): fragments resident so far
+    u32* done;             // streamed output: finished fragments per chunk of done_div
+    u32 done_div;
+    u32 lib_rules;         // kLib: 1 = libsnappy <= 1.1.7 (hash >> shift, <= 16384 buckets), 2 = Google snappy >= 1.1.9
+    const u32* order;      // the k-th fragment pulled is order[k] (schedule.cuh); the bytes do not depend on it
+    u64* trace;            // option `trace`
+};
+
+// The life of one persistent warp: pull a fragment, clear the table, run the window rounds, record the size.
+//   T / ring : this warp's table (shared or global memory) and ring (shared-space address)
+//   kLib (option `rules`): libsnappy's rules, table sized per fragment; rules = 2: 64 KiB tables.
+template <bool kSmemTable, bool kLib, bool kSlowCont>
+__device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u32 ring, u32 ring_bytes, u32 tab,
+                                                 u32 reserve) {
     const u32 lane = lane_id();
+    const u32 nfrag = A.nfrag;
     for (;;) {
-        if (reserve && *reinterpret_cast<volatile u32*>(counter) + reserve >= nfrag) break;
+        if (reserve && *reinterpret_cast<volatile u32*>(A.counter) + reserve >= nfrag) break;
         u32 frag = 0;
-        if (lane == 0) frag = atomicAdd(counter, 1u);
+        if (lane == 0) frag = atomicAdd(A.counter, 1u);
         frag = __shfl_sync(kFullMask, frag, 0);
         if (frag >= nfrag) break;
-        if (order) frag = order[frag];  // schedule.cuh: expensive fragments first (never together with `ready`)
+        if (A.order) frag = A.order[frag];  // schedule.cuh: expensive fragments first (never together with `ready`)
         u64 t_begin = 0;
-        if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-        if (ready) {  // streamed input (host-buffer API): wait until this fragment and the one behind it
-                      // (the kernel reads a few bytes past a fragment's end) have landed
+#ifndef SB200_CPU_EMU
+        if (A.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
+        if (A.ready) {  // streamed input (host-buffer API): wait until this fragment and the one behind it
+                        // (the kernel reads a few bytes past a fragment's end) have landed
             if (lane == 0) {
                 const u32 need = frag + 2u < nfrag ? frag + 2u : nfrag;
-                while (*reinterpret_cast<const volatile u32*>(ready) < need) __nanosleep(500);
+                while (*reinterpret_cast<const volatile u32*>(A.ready) < need) __nanosleep(500);
             }
             __syncwarp();
         }
-        const u8* sbase = g_in;
-        const u8* stail = tail_copy;
-        u64 slen = shard_len;
-        u32 local = frag, lastf = nfrag - 1, fshift = shift;
-        if (descs) {
+        const u8* sbase = A.g_in;
+        const u8* stail = A.tail_copy;
+        u64 slen = A.shard_len;
+        u32 local = frag, lastf = nfrag - 1, fshift = A.shift;
+        if (A.descs) {
             u32 k = 0;
-            while (k + 1 < ndesc && descs[k + 1].frag_begin <= frag) k++;
-            sbase = descs[k].ptr;
-            stail = descs[k].tail;
-            slen = descs[k].len;
-            local = frag - descs[k].frag_begin;
-            lastf = descs[k].nfrag - 1;
-            fshift = descs[k].shift;
+            while (k + 1 < A.ndesc && A.descs[k + 1].frag_begin <= frag) k++;
+            sbase = A.descs[k].ptr;
+            stail = A.descs[k].tail;
+            slen = A.descs[k].len;
+            local = frag - A.descs[k].frag_begin;
+            lastf = A.descs[k].nfrag - 1;
+            fshift = A.descs[k].shift;
         }
         const u64 start = (u64)local * kBlockSize;
         const u32 n = (u32)((slen - start < kBlockSize) ? (slen - start) : kBlockSize);
@@ -472,7 +482,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         if (kLib) {  // GetHashTable: sized from THIS fragment's length
             entries = 256;
             while (entries < tab && entries < n) entries <<= 1;
-            fshift = lib_rules == 2u ? 17u : (u32)__clz((int)entries) + 1u;  // 32 - log2(entries)
+            fshift = A.lib_rules == 2u ? 17u : (u32)__clz((int)entries) + 1u;  // 32 - log2(entries)
         }
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
@@ -482,7 +492,7 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;
         ch.Ts = kSmemTable ? smem_u32(T) : 0u;
-        ch.out = scratch + (u64)frag * kSlotStride;
+        ch.out = A.scratch + (u64)frag * kSlotStride;
         ch.n = n;
         ch.shift = fshift;
         ch.lane = lane;
@@ -494,20 +504,145 @@ k_compress_window(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shi
         ch.nstage = (n + kRingChunk - 1u) & ~(kRingChunk - 1u);
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
         ch.run_window();
-        if (lane == 0) frag_sizes[frag] = ch.op;
-        if (trace && lane == 0) {  // option `trace`: [begin ns | table placement in bit 0, end ns | SM in the low 8 bits]
-            u64 t_end;
-            u32 smid;
+        if (lane == 0) A.frag_sizes[frag] = ch.op;
+        if (A.trace && lane == 0) {  // option `trace`: [begin ns | table placement in bit 0, end ns | SM in the low 8 bits]
+            u64 t_end = 0;
+            u32 smid = 0;
+#ifndef SB200_CPU_EMU
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            trace[2 * (u64)frag] = (t_begin & ~(u64)1) | (kSmemTable ? 1u : 0u);
-            trace[2 * (u64)frag + 1] = (t_end & ~(u64)0xff) | (smid & 0xffu);
+#endif
+            A.trace[2 * (u64)frag] = (t_begin & ~(u64)1) | (kSmemTable ? 1u : 0u);
+            A.trace[2 * (u64)frag + 1] = (t_end & ~(u64)0xff) | (smid & 0xffu);
         }
-        if (done) {  // streamed output: per-chunk completion counts release the compaction of a chunk
+        if (A.done) {  // streamed output: per-chunk completion counts release the compaction of a chunk
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicAdd(done + frag / done_div, 1u);
+            if (lane == 0) atomicAdd(A.done + frag / A.done_div, 1u);
         }
+        __syncwarp();
+    }
+}
+
+// One table placement per launch: every warp of the CTA owns a table (behind each other in shared memory, or in
+// `gtables`) and `ring_bytes` of shared memory for its ring.  Used alone when the other placement is switched off.
+template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
+__global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
+k_compress_window(const WindowArgs A, u32 ring_bytes) {
+    extern __shared__ __align__(128) u8 smem[];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarp = blockDim.x >> 5;
+    const u32 gwarp = blockIdx.x * nwarp + warp;
+    const u32 tab = kLib ? (A.lib_rules == 2u ? 2u * kMaxTableEntries : kMaxTableEntries) : kMaxTableEntries;
+    u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * tab : A.gtables + (size_t)gwarp * tab;
+    const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * tab * 2u : 0u) + warp * (ring_bytes + kRingMirror);
+    window_warp_loop<kSmemTable, kLib, kSlowCont>(A, T, ring, ring_bytes, tab, kSmemTable ? 0u : A.reserve);
+}
+
+// Both table placements in ONE CTA per SM (the default): warps [0, wb) keep their table in global memory (L2),
+// warps [wb, wb + wa) in shared memory.  The shared-table warps are the latency-bound ones (a lone dependent
+// instruction stream each) and take the HIGHER warp numbers: the issue arbiter prefers higher warp slots, and as two
+// separate kernels the shared-table CTA -- launched first, lower slots -- lost issue slots to the 14 global-table
+// warps next to it (a text fragment took 3.6 ms on a shared-table warp with the other kernel running, 2.0 ms alone;
+// profiles/r02b_trace_fragments.txt).  One kernel is also what lets ncu measure the pair as it really runs.
+// Shared memory: wa tables, then wa rings of ring_a bytes, then wb rings of ring_b bytes.
+template <bool kLib = false>
+__global__ void __launch_bounds__(704, 1)
+k_compress_window_mixed(const WindowArgs A, u32 wa, u32 wb, u32 ring_a, u32 ring_b, u32 smem_first) {
+    extern __shared__ __align__(128) u8 smem[];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 tab = kLib ? (A.lib_rules == 2u ? 2u * kMaxTableEntries : kMaxTableEntries) : kMaxTableEntries;
+    const u32 rings = smem_u32(smem) + wa * tab * 2u;
+    // smem_first (experiment): the shared-table warps take the LOW warp numbers instead
+    const bool is_smem = smem_first ? warp < wa : warp >= wb;
+    if (is_smem) {
+        const u32 w = smem_first ? warp : warp - wb;
+        u16* T = reinterpret_cast<u16*>(smem) + (size_t)w * tab;
+        window_warp_loop<true, kLib, false>(A, T, rings + w * (ring_a + kRingMirror), ring_a, tab, 0u);
+    } else {
+        const u32 w = smem_first ? warp - wa : warp;
+        u16* T = A.gtables + ((size_t)blockIdx.x * wb + w) * tab;
+        window_warp_loop<false, kLib, false>(A, T, rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror),
+                                             ring_b, tab, A.reserve);
+    }
+}
+
+// K1bw: batched pages (one independent stream per page, src/Snappy.jl:20-36 per page) with the window round.
+// Persistent warps pull pages from a counter; a warp holds its page's hash table AND the whole page in shared
+// memory (the ring is as large as the largest page, so every candidate is "near": no global gathers at all), which
+// limits this kernel to pages of at most ring_bytes <= 8 KiB (larger pages keep k_compress_pages).  The page's own
+// varint header goes in front (varint.jl:46-69), the table is sized from the page length (Snappy.jl:27).
+// 4 KiB pages: 8 KiB table + 4 KiB ring per warp, 16 warps per SM.
+template <bool kLib = false>
+__global__ void __launch_bounds__(512, 1)
+k_compress_pages_window(const u8* __restrict__ g_in, const u64* __restrict__ in_off, const u32* __restrict__ in_size,
+                        u32 count, u8* __restrict__ g_out, const u64* __restrict__ out_off, u32* __restrict__ out_size,
+                        u32 ring_bytes, u32 table_cap, u32* __restrict__ counter, u32 lib_rules = 0) {
+    extern __shared__ __align__(128) u8 smem[];
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarp = blockDim.x >> 5;
+    const u32 lane = lane_id();
+    u16* T = reinterpret_cast<u16*>(smem) + (size_t)warp * table_cap;
+    u8* R = smem + (size_t)nwarp * table_cap * 2u + (size_t)warp * (ring_bytes + kRingMirror);
+    for (;;) {
+        u32 pg = 0;
+        if (lane == 0) pg = atomicAdd(counter, 1u);
+        pg = __shfl_sync(kFullMask, pg, 0);
+        if (pg >= count) break;
+        const u8* pin = g_in + in_off[pg];
+        const u32 n = in_size[pg];
+        u8* pout = g_out + out_off[pg];
+        u32 hdr = 0;
+        {   // varint header, src/varint.jl:46-69
+            u32 v = n;
+            while (v >= 0x80) {
+                if (lane == 0) pout[hdr] = (u8)(v | 0x80);
+                v >>= 7;
+                hdr++;
+            }
+            if (lane == 0) pout[hdr] = (u8)v;
+            hdr++;
+        }
+        u32 entries = 256;  // alloc_hashtable, src/internal.jl:107-113 (kLib: GetHashTable, the same for one fragment)
+        while (entries < table_cap && entries < n) entries <<= 1;
+        u32 fshift = (u32)__clz((int)entries) + 1u;  // 32 - log2(entries)
+        if (kLib && lib_rules == 2u) fshift = 17u;
+        uint4* t4 = reinterpret_cast<uint4*>(T);
+        for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+        // the whole page into the ring (zero behind its end), the ring's first bytes again behind the ring
+        const bool al = (reinterpret_cast<uintptr_t>(pin) & 15u) == 0;
+        for (u32 i = lane * 16u; i < ring_bytes; i += 512u) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i + 16u <= n && al) {
+                v = __ldg(reinterpret_cast<const uint4*>(pin + i));
+            } else if (i < n) {
+                u32 w[4] = {0, 0, 0, 0};
+                for (u32 k = 0; k < 16u && i + k < n; k++) w[k >> 2] |= (u32)__ldg(pin + i + k) << (8u * (k & 3u));
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(R + i) = v;
+            if (i < kRingMirror) *reinterpret_cast<uint4*>(R + ring_bytes + i) = v;
+        }
+        __syncwarp();
+        Win<true, kLib> ch;
+        ch.hmask = entries - 1u;
+        ch.F = pin;
+        ch.T = T;
+        ch.Ts = smem_u32(T);
+        ch.out = pout + hdr;
+        ch.n = n;
+        ch.shift = fshift;
+        ch.lane = lane;
+        ch.spec = 0;
+        ch.Rs = smem_u32(R);
+        ch.rmask = ring_bytes - 1u;
+        ch.lo = 0;
+        ch.hi = 0x7fffff00u;  // everything is resident: the round never stages, every candidate is near
+        ch.pre_at = 0xffffffffu;
+        ch.nstage = 0;
+        ch.aligned16 = false;
+        ch.run_window();
+        if (lane == 0) out_size[pg] = hdr + ch.op;
         __syncwarp();
     }
 }

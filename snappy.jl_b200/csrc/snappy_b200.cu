@@ -56,6 +56,7 @@ struct DevBuf {
 
 constexpr int kMaxPipeChunks = 72;                 // 4 GiB / 64 MiB, plus slack
 constexpr size_t kPinnedBytes = 64 * 1024;         // small pinned readback area of a lane
+constexpr u32 kPageWindowMax = 8192;               // batched pages up to this size take the window-round page kernel
 constexpr size_t kPinnedShardLens = 8192;          // offset of the per-shard lengths of the batched shard API (<= 4096 x u64)
 constexpr size_t kPipeChunkFragsDefault = 4096;    // fragments per pipeline chunk (256 MiB)
 
@@ -86,6 +87,10 @@ struct Options {
     int timing = 1;             // record CUDA events around the dominant kernel
     int trace = 0;              // 1 = the compress warps record begin / end time of every fragment (snappy_b200_debug_trace)
     int profile_range = 0;      // 1 = cudaProfilerStart/Stop around the concurrent compress kernels (ncu --replay-mode range)
+    int mixed = 1;              // 1 = both table placements in ONE kernel, shared-table warps on the high warp numbers;
+                                // 2 = the same with them on the low ones; 0 = two concurrent kernels (round 1)
+    int l2_first = 0;           // mixed = 0 only: launch the global-table kernel before the shared-table kernel
+    int pages_window = 1;       // batched pages <= 8 KiB: window-round kernel (0 = the serial page kernel for every size)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
     int pin_host = 1;           // host-buffer API on pageable memory: register the caller's buffers for the call
 };
@@ -193,6 +198,9 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "decode_occupancy")) g_opt.decode_occupancy = value;
     else if (!strcmp(name, "timing")) g_opt.timing = value;
     else if (!strcmp(name, "lpt")) g_opt.lpt = value;
+    else if (!strcmp(name, "pages_window")) g_opt.pages_window = value;
+    else if (!strcmp(name, "mixed")) g_opt.mixed = value;
+    else if (!strcmp(name, "l2_first")) g_opt.l2_first = value;
     else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
     else if (!strcmp(name, "trace")) g_opt.trace = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
@@ -204,6 +212,10 @@ int set_kernel_attributes() {
                             (int)kCompressSmemBytes));
     CU(cudaFuncSetAttribute(k_compress_pages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kCompressSmemBytes + kMaxTableEntries * 2)));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_pages_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_pages_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // both window kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
     // CTAs fit next to the shared-table CTA
     CU(cudaFuncSetAttribute(k_compress_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -518,29 +530,50 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
     const bool window = c.opt.window != 0 || rules != 0;
     (void)window;
     const u32 ra = (u32)c.opt.ring_smem, rb = (u32)c.opt.ring_l2;
-    if (ctas_a) {
-        if (rules)
-            k_compress_window<true, true><<<ctas_a, wa * 32, (size_t)wa * (tab_bytes + ra + kRingMirror), st>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, rules, order, trace);
+    WindowArgs A;
+    memset(&A, 0, sizeof A);
+    A.g_in = d_in;
+    A.shard_len = (u64)len;
+    A.nfrag = nfrag;
+    A.shift = shift;
+    A.tail_copy = (const u8*)c.tail.p;
+    A.scratch = scratch;
+    A.frag_sizes = sizes;
+    A.counter = counter;
+    A.gtables = (u16*)c.gtables.p;
+    A.reserve = reserve;
+    A.descs = descs;
+    A.ndesc = ndesc;
+    A.ready = gate ? gate->ready : nullptr;
+    A.done = gate ? gate->done : nullptr;
+    A.done_div = gate ? gate->div : 1u;
+    A.lib_rules = rules;
+    A.order = order;
+    A.trace = trace;
+    const size_t smem_a = (size_t)wa * (tab_bytes + ra + kRingMirror), smem_b = (size_t)wb * (rb + kRingMirror);
+    bool plain = true;
 #ifdef SB200_EXPERIMENTS
-        else if (window && c.opt.slowcont)
-            k_compress_window<true, false, true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u);
-        else if (!window)
-            k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
-                (u32)c.opt.spec_smem, 0u, descs, ndesc);
+    plain = !(window && c.opt.slowcont) && window;
 #endif
+    if (plain && ctas_a && ctas_b && c.opt.mixed && c.opt.l2_ctas == 1 && wa + wb <= 22 && smem_a + smem_b <= 227 * 1024) {
+        // the default: both table placements in one CTA per SM (the global-table rows of `gtables` are indexed by
+        // CTA, so the grid is the shared-table grid: one CTA per SM)
+        if (rules)
+            k_compress_window_mixed<true><<<c.sm_count, (wa + wb) * 32, smem_a + smem_b, st>>>(
+                A, wa, wb, ra, rb, c.opt.mixed == 2 ? 1u : 0u);
         else
-            k_compress_window<true><<<ctas_a, wa * 32, (size_t)wa * (kMaxTableEntries * 2 + ra + kRingMirror), st>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr, 0u, descs,
-                ndesc, ra, gate ? gate->ready : nullptr, gate ? gate->done : nullptr, gate ? gate->div : 1u, 0u, order, trace);
+            k_compress_window_mixed<false><<<c.sm_count, (wa + wb) * 32, smem_a + smem_b, st>>>(
+                A, wa, wb, ra, rb, c.opt.mixed == 2 ? 1u : 0u);
+        *launches += 1;
+        if (prof) {
+            CU(cudaStreamSynchronize(st));
+            cudaProfilerStop();
+        }
+        return SNAPPY_B200_OK;
     }
-    *launches += 1;
-    if (ctas_b) {
-        CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    const bool l2_first = c.opt.l2_first != 0 && ctas_a && ctas_b;
+    if (ctas_b && l2_first) CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    auto launch_b = [&]() -> int {
         if (c.opt.l2_persist && c.l2_persist_max && c.l2_window_max) {
             // keep the global hash tables resident in L2: they are the randomly read-and-written state, the
             // fragment bytes stream through the rest of the cache
@@ -556,26 +589,44 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             CU(cudaStreamSetAttribute(c.side, cudaStreamAttributeAccessPolicyWindow, &av));
         }
         if (rules)
-            k_compress_window<false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
-                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u, rules, order, trace);
+            k_compress_window<false, true><<<ctas_b, wb * 32, smem_b, c.side>>>(A, rb);
 #ifdef SB200_EXPERIMENTS
         else if (window && c.opt.slowcont)
-            k_compress_window<false, false, true><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
-                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u);
+            k_compress_window<false, false, true><<<ctas_b, wb * 32, smem_b, c.side>>>(A, rb);
         else if (!window)
             k_compress_chain<false><<<ctas_b, wb * 32, 0, c.side>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
                 (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
 #endif
         else
-            k_compress_window<false><<<ctas_b, wb * 32, (size_t)wb * (rb + kRingMirror), c.side>>>(
-                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, (u16*)c.gtables.p,
-                reserve, descs, ndesc, rb, gate ? gate->ready : nullptr, gate ? gate->done : nullptr,
-                gate ? gate->div : 1u, 0u, order, trace);
+            k_compress_window<false><<<ctas_b, wb * 32, smem_b, c.side>>>(A, rb);
+        return SNAPPY_B200_OK;
+    };
+    if (ctas_b && l2_first) {  // experiment: the global-table CTAs take the lower warp slots of every SM
+        int r = launch_b();
+        if (r != SNAPPY_B200_OK) return r;
+    }
+    if (ctas_a) {
+        if (rules)
+            k_compress_window<true, true><<<ctas_a, wa * 32, smem_a, st>>>(A, ra);
+#ifdef SB200_EXPERIMENTS
+        else if (window && c.opt.slowcont)
+            k_compress_window<true, false, true><<<ctas_a, wa * 32, smem_a, st>>>(A, ra);
+        else if (!window)
+            k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
+                d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
+                (u32)c.opt.spec_smem, 0u, descs, ndesc);
+#endif
+        else
+            k_compress_window<true><<<ctas_a, wa * 32, smem_a, st>>>(A, ra);
+    }
+    *launches += 1;
+    if (ctas_b) {
+        if (!l2_first) {
+            CU(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+            int r = launch_b();
+            if (r != SNAPPY_B200_OK) return r;
+        }
         CU(cudaEventRecord(c.ev_join, c.side));
         CU(cudaStreamWaitEvent(st, c.ev_join, 0));
         *launches += 1;
@@ -1624,7 +1675,24 @@ int snappy_b200_compress_batched_device(const uint8_t* d_in, const uint64_t* d_i
     while (entries < (rules == 2 ? 2u : 1u) * kMaxTableEntries && entries < max_size) entries <<= 1;
     const size_t smem = (size_t)frag_cap + kFragPad + (size_t)entries * 2 + 16;
     if (c.opt.timing) CU(cudaEventRecord(c.ev[0], st));
-    if (rules)
+    if (c.opt.pages_window && max_size <= kPageWindowMax) {
+        // small pages: the window round, table and whole page in shared memory, persistent warps (K1bw)
+        u32 ring = 1024;
+        while (ring < max_size) ring <<= 1;
+        const size_t per_warp = (size_t)entries * 2 + ring + kRingMirror;
+        u32 warps = (u32)((226 * 1024) / per_warp);
+        if (warps > 16) warps = 16;
+        u32 ctas = (u32)((count + warps - 1) / warps);
+        if (ctas > (u32)c.sm_count) ctas = (u32)c.sm_count;
+        u32* counter = (u32*)((u8*)c.result.p + 64);
+        CU(cudaMemsetAsync(counter, 0, 4, st));
+        if (rules)
+            k_compress_pages_window<true><<<ctas, warps * 32, warps * per_warp, st>>>(
+                d_in, d_in_offsets, d_in_sizes, (u32)count, d_out, d_out_offsets, d_out_sizes, ring, entries, counter, rules);
+        else
+            k_compress_pages_window<false><<<ctas, warps * 32, warps * per_warp, st>>>(
+                d_in, d_in_offsets, d_in_sizes, (u32)count, d_out, d_out_offsets, d_out_sizes, ring, entries, counter);
+    } else if (rules)
         k_compress_pages<true><<<(unsigned)count, 32, smem, st>>>(d_in, d_in_offsets, d_in_sizes, d_out, d_out_offsets,
                                                                   d_out_sizes, frag_cap, entries, rules);
     else
@@ -1795,7 +1863,7 @@ int snappy_b200_get_option(const char* name) {
         {"host_pipeline", o.host_pipeline}, {"timing", o.timing}, {"l2_persist", o.l2_persist},
         {"overlap_compact", o.overlap_compact}, {"window", o.window}, {"wide", o.wide}, {"slowcont", o.slowcont},
         {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host}, {"trace", o.trace},
-        {"profile_range", o.profile_range},
+        {"profile_range", o.profile_range}, {"pages_window", o.pages_window}, {"mixed", o.mixed}, {"l2_first", o.l2_first},
     };
     for (const auto& e : tab)
         if (!strcmp(name, e.n)) return e.v;

@@ -26,8 +26,9 @@ def warp(tmp_path_factory):
     return exe
 
 
-def run(exe, files, table, rules, ring, kernel="window", slowcont=0):
-    env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel, SLOWCONT=str(slowcont))
+def run(exe, files, table, rules, ring, kernel="window", slowcont=0, mixed=0):
+    env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel, SLOWCONT=str(slowcont),
+               MIXED=str(mixed))
     p = subprocess.run([exe] + files, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     lines = [l for l in p.stdout.splitlines() if "fragments" in l]
@@ -40,6 +41,14 @@ def run(exe, files, table, rules, ring, kernel="window", slowcont=0):
 @pytest.mark.parametrize("rules", [0, 1, 2])
 def test_kernel_source_matches_oracle_on_fixtures(warp, table, ring, rules):
     run(warp, [os.path.join(DATA, f) for f in FILES], table, rules, ring)
+
+
+@pytest.mark.parametrize("table,ring", [("smem", 2048), ("global", 1024)])
+@pytest.mark.parametrize("rules", [0, 2])
+def test_mixed_kernel_source_matches_oracle_on_fixtures(warp, table, ring, rules):
+    """k_compress_window_mixed, the default launch form: one CTA holds both table placements (global-table warps on
+    the low warp numbers, shared-table warps on the high ones); the harness runs either role of a two-warp CTA"""
+    run(warp, [os.path.join(DATA, f) for f in FILES], table, rules, ring, mixed=1)
 
 
 def test_kernel_source_on_boundary_sizes_and_patterns(warp, tmp_path):
@@ -187,6 +196,25 @@ def test_page_kernel_sources_match_oracle_and_round_trip(tmp_path, rules):
                            "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_pages_kernel.cpp"), obj])
     files = [os.path.join(DATA, f) for f in ("html", "alice29.txt", "fireworks.jpeg", "sample-tweet.json", "geo.protodata")]
     p = subprocess.run([exe] + files, env=dict(os.environ, RULES=str(rules)), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert len(lines) == len(files)
+    for l in lines:
+        assert "0 mismatches" in l, l
+
+
+@pytest.mark.parametrize("rules,page", [(0, 4096), (2, 4096), (0, 1000), (0, 8192), (1, 5000)])
+def test_page_window_kernel_source_matches_oracle_and_round_trips(tmp_path, rules, page):
+    """k_compress_pages_window (pages <= 8 KiB: window round, table and whole page in shared memory, persistent warp):
+    every page's stream equals the oracle's compress of that page; ragged and empty pages included"""
+    exe = str(tmp_path / "run_pages_kernel")
+    obj = str(tmp_path / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-DSB200_EXPERIMENTS", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_pages_kernel.cpp"), obj])
+    files = [os.path.join(DATA, f) for f in ("html", "alice29.txt", "fireworks.jpeg", "sample-tweet.json", "kppkn.gtb")]
+    p = subprocess.run([exe] + files, env=dict(os.environ, RULES=str(rules), PAGE=str(page), KERNEL="window"),
+                       capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     lines = p.stdout.splitlines()
     assert len(lines) == len(files)

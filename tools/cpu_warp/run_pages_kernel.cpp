@@ -6,6 +6,7 @@
 // k_decode_pages and compared with the input.  The fragment staging (TMA bulk copy + mbarrier on the GPU) is a plain
 // copy under SB200_CPU_EMU.
 #include "../../snappy.jl_b200/csrc/compress.cuh"
+#include "../../snappy.jl_b200/csrc/compress_window.cuh"
 #include "../../snappy.jl_b200/csrc/decompress.cuh"
 
 #include <vector>
@@ -28,6 +29,23 @@ struct CArgs {
     u32* out_size;
     u32 frag_cap, table_cap, rules;
 };
+struct WArgs {  // k_compress_pages_window (KERNEL=window): persistent warp, pages pulled from *counter
+    const u8* in;
+    const u64* in_off;
+    const u32* in_size;
+    u32 count;
+    u8* out;
+    const u64* out_off;
+    u32* out_size;
+    u32 ring, table_cap;
+    u32* counter;
+    u32 rules;
+};
+static void entry_window(void* p) {
+    const WArgs& a = *(const WArgs*)p;
+    if (a.rules) k_compress_pages_window<true>(a.in, a.in_off, a.in_size, a.count, a.out, a.out_off, a.out_size, a.ring, a.table_cap, a.counter, a.rules);
+    else k_compress_pages_window<false>(a.in, a.in_off, a.in_size, a.count, a.out, a.out_off, a.out_size, a.ring, a.table_cap, a.counter, 0u);
+}
 static void entry_compress(void* p) {
     const CArgs& a = *(const CArgs*)p;
     if (a.rules) k_compress_pages<true>(a.in, a.in_off, a.in_size, a.out, a.out_off, a.out_size, a.frag_cap, a.table_cap, a.rules);
@@ -49,9 +67,15 @@ static void entry_decode(void* p) {
     k_decode_pages(a.in, a.in_off, a.in_size, a.count, a.out, a.out_off, a.out_cap, a.out_size, a.statuses);
 }
 
+static void entry_init(void*) { k_init_probe_offsets(); }
+
 int main(int argc, char** argv) {
+    cpu_warp::W().block = cpu_warp::W().tid_base = 0;
+    cpu_warp::W().block_dim = 32;
+    cpu_warp::run_warp(entry_init, nullptr);  // the skip-heuristic probe offsets (a __device__ table on the GPU)
     const u32 rules = getenv("RULES") ? (u32)atoi(getenv("RULES")) : 0u;
     const u32 page = getenv("PAGE") ? (u32)atoi(getenv("PAGE")) : 4096u;
+    const bool window = getenv("KERNEL") && !strcmp(getenv("KERNEL"), "window");  // pages <= 8 KiB only
     int failed = 0;
     for (int ai = 1; ai < argc; ai++) {
         FILE* fp = fopen(argv[ai], "rb");
@@ -79,7 +103,7 @@ int main(int argc, char** argv) {
             if (k % 29 == 11) n = 0;
             add(raw.data() + o, n);
         }
-        add(raw.data(), sz < 150000 ? sz : 150000);  // one multi-fragment page
+        if (!window) add(raw.data(), sz < 150000 ? sz : 150000);  // one multi-fragment page
         flat.resize(flat.size() + 256, 0);
         const u32 count = (u32)in_size.size();
         u32 max_size = 0;
@@ -98,15 +122,37 @@ int main(int argc, char** argv) {
         CArgs ca{flat.data(), in_off.data(), in_size.data(), out.data(), out_off.data(), out_size.data(), frag_cap, entries, rules};
         long bad = 0;
         std::vector<u8> want(sjo_maxlength_compressed(max_size) + 64);
+        if (window) {  // one persistent warp compresses every page (the CTA's warps never talk to each other)
+            u32 ring = 1024;
+            while (ring < max_size) ring <<= 1;
+            if (getenv("RINGX")) ring *= (u32)atoi(getenv("RINGX"));
+            u32 counter = 0;
+            WArgs wa{flat.data(), in_off.data(), in_size.data(), count, out.data(), out_off.data(), out_size.data(),
+                     ring, entries, &counter, rules};
+            cpu_warp::W().block = 0;
+            cpu_warp::W().tid_base = 32;   // warp 1 of a 2-warp CTA: table and ring are not at the start of smem
+            cpu_warp::W().block_dim = 64;
+            cpu_warp::run_warp(entry_window, &wa);
+        }
         for (u32 i = 0; i < count; i++) {
-            cpu_warp::W().block = i;
-            cpu_warp::W().tid_base = 0;
-            cpu_warp::W().block_dim = 32;
-            cpu_warp::run_warp(entry_compress, &ca);
+            if (!window) {
+                cpu_warp::W().block = i;
+                cpu_warp::W().tid_base = 0;
+                cpu_warp::W().block_dim = 32;
+                cpu_warp::run_warp(entry_compress, &ca);
+            }
             size_t wl = want.size();
             if (sjo_compress_rules(flat.data() + in_off[i], in_size[i], want.data(), &wl, (int)rules) != SJO_OK) return 2;
             if (wl != out_size[i] || memcmp(want.data(), out.data() + out_off[i], wl)) {
-                if (bad++ < 3) fprintf(stderr, "%s: page %u (%u bytes) differs (%u vs %zu)\n", argv[ai], i, in_size[i], out_size[i], wl);
+                if (bad++ < 3) {
+                    fprintf(stderr, "%s: page %u (%u bytes) differs (%u vs %zu)\n", argv[ai], i, in_size[i], out_size[i], wl);
+                    if (getenv("DUMP")) {
+                        for (u32 k = 0; k < 48; k++) fprintf(stderr, "%02x ", out[out_off[i] + k]);
+                        fprintf(stderr, "\n");
+                        for (u32 k = 0; k < 48; k++) fprintf(stderr, "%02x ", want[k]);
+                        fprintf(stderr, "\n");
+                    }
+                }
             }
         }
         // decode every page from the kernel's own output

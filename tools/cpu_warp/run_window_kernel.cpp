@@ -29,12 +29,33 @@ struct Args {
     u32 ring, rules;
     bool chain;  // KERNEL=chain: the step-wise kernel (option window=0), rules 0 only
     bool slowcont;  // SLOWCONT=1: the experimental window variant (option slowcont), rules 0 only
+    bool mixed;     // MIXED=1: k_compress_window_mixed (one CTA holds both table placements)
 };
 
+static WindowArgs wargs(const Args& a) {
+    WindowArgs w;
+    memset(&w, 0, sizeof w);
+    w.g_in = a.in;
+    w.shard_len = a.len;
+    w.nfrag = a.nfrag;
+    w.shift = a.shift;
+    w.tail_copy = a.tail;
+    w.scratch = a.scratch;
+    w.frag_sizes = a.sizes;
+    w.counter = a.counter;
+    w.gtables = a.gtables;
+    w.done_div = 1;
+    w.lib_rules = a.rules;
+    return w;
+}
 template <bool kSmem, bool kLib>
 static void launch(const Args& a) {
-    k_compress_window<kSmem, kLib>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables, 0u,
-                                   nullptr, 0u, a.ring, nullptr, nullptr, 1u, a.rules);
+    if (a.mixed) {  // the default launch form: both placements in one CTA; this warp plays the role TABLE names
+        // CTA of wb = 1 global-table warp and wa = 1 shared-table warp: warp 0 / warp 1 (the harness sets tid_base)
+        k_compress_window_mixed<kLib>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        return;
+    }
+    k_compress_window<kSmem, kLib>(wargs(a), a.ring);
 }
 static void entry(void* p) {
     const Args& a = *(const Args*)p;
@@ -45,11 +66,9 @@ static void entry(void* p) {
     }
     if (a.slowcont) {
         if (a.smem_table)
-            k_compress_window<true, false, true>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables,
-                                                  0u, nullptr, 0u, a.ring, nullptr, nullptr, 1u, 0u);
+            k_compress_window<true, false, true>(wargs(a), a.ring);
         else
-            k_compress_window<false, false, true>(a.in, a.len, a.nfrag, a.shift, a.tail, a.scratch, a.sizes, a.counter, a.gtables,
-                                                   0u, nullptr, 0u, a.ring, nullptr, nullptr, 1u, 0u);
+            k_compress_window<false, false, true>(wargs(a), a.ring);
         return;
     }
     if (a.smem_table) {
@@ -68,6 +87,7 @@ int main(int argc, char** argv) {
     const u32 ring = getenv("RING") ? (u32)atoi(getenv("RING")) : 2048u;
     const bool chain = getenv("KERNEL") && !strcmp(getenv("KERNEL"), "chain");
     const bool slowcont = getenv("SLOWCONT") && atoi(getenv("SLOWCONT")) != 0;
+    const bool mixed = getenv("MIXED") && atoi(getenv("MIXED")) != 0;
     if ((chain || slowcont) && rules) {
         fprintf(stderr, "KERNEL=chain has no rules instantiation\n");
         return 2;
@@ -103,8 +123,13 @@ int main(int argc, char** argv) {
         u32 counter = 0;
         u32 entries = sjo_hashtable_entries((u64)sz), shift = 32;
         for (u32 e = entries; e > 1; e >>= 1) shift--;
-        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont};
+        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont, mixed};
         cpu_warp::W().collectives = 0;
+        if (mixed) {  // CTA of two warps: warp 0 = global-table role, warp 1 = shared-table role
+            cpu_warp::W().block = 0;
+            cpu_warp::W().tid_base = smem_table ? 32 : 0;
+            cpu_warp::W().block_dim = 64;
+        }
         cpu_warp::run_warp(entry, &a);
         // the oracle, fragment by fragment
         u8* want = (u8*)malloc(kSlotStride);
