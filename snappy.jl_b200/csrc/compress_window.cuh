@@ -37,7 +37,12 @@
 namespace sb200 {
 
 constexpr u32 kRingChunk = 512;  // bytes staged per step (one 16-byte load per lane)
-constexpr u32 kRingAhead = 64;   // bytes past the window start that must be resident
+// SB200_PREFETCH (experiment): 1 = shared-table warps, 2 = all warps look the NEXT window's positions up in the table
+// as well and prefetch their far candidates into L2 (a hint: the lookups are repeated next round)
+#ifndef SB200_PREFETCH
+#define SB200_PREFETCH 0
+#endif
+constexpr u32 kRingAhead = SB200_PREFETCH ? 96 : 64;   // bytes past the window start that must be resident
 constexpr u32 kRingMirror = 32;  // the first bytes of the ring are repeated behind its end: a 20-byte read never wraps
 #ifndef SB200_FAR_ALL
 #define SB200_FAR_ALL 1
@@ -92,6 +97,14 @@ struct Win : Chain<kSmemTable, kLib> {
     __device__ __forceinline__ uint4 load_chunk(u32 p) const {
         uint4 v;
         if (aligned16) {
+#if defined(SB200_STAGE_EL) && !defined(SB200_CPU_EMU)
+            // experiment: the staged chunk's lines get the L2 evict_last priority (1: every warp, 2: shared-table warps)
+            if (SB200_STAGE_EL == 1 || kSmemTable)
+                asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; "
+                             "ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol; }"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(F + p) : "memory");
+            else
+#endif
             v = __ldg(reinterpret_cast<const uint4*>(F + p));
         } else {
             v.x = ldg32u(F + p);
@@ -215,6 +228,10 @@ struct Win : Chain<kSmemTable, kLib> {
                 }
                 const u32 H = this->hash(B0);
                 const u32 t = V ? this->tget(H) : lo;
+#if SB200_PREFETCH && !defined(SB200_CPU_EMU)
+                u32 t_next = 0xffffffffu;  // candidate of position q + 32 by the table as it is now
+                if ((kSmemTable || SB200_PREFETCH >= 2) && (int)(q + 32u) < lim) t_next = this->tget(this->hash(ring32u(q + 32u)));
+#endif
                 const u32 mp = __match_any_sync(kFullMask, V ? H : (0x80000000u | lane));
                 // candidate bytes, straight-line: recent candidates come from the ring (5 words), old
                 // ones from L1/L2 (2 words = the 4 bytes that decide a hit; the other 3 only on a hit)
@@ -235,6 +252,32 @@ struct Win : Chain<kSmemTable, kLib> {
                     if (far_all) { c2 = g[2]; c3 = g[3]; c4 = g[4]; }
                 }
 #else
+#if defined(SB200_FAR_EF)
+                // experiment: far candidates of the global-table warps leave L2 first (evict_first), so that they do
+                // not push out the lines the shared-table warps gather from
+                if (!kSmemTable) {
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p;\n"
+                        ".reg .b64 pol;\n"
+                        "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
+                        "setp.ne.u32 p, %5, 0;\n"
+                        "@p ld.shared.u32 %0, [%6];\n"
+                        "@p ld.shared.u32 %1, [%6+4];\n"
+                        "@p ld.shared.u32 %2, [%6+8];\n"
+                        "@p ld.shared.u32 %3, [%6+12];\n"
+                        "@p ld.shared.u32 %4, [%6+16];\n"
+                        "@!p ld.global.nc.L2::cache_hint.u32 %0, [%7], pol;\n"
+                        "@!p ld.global.nc.L2::cache_hint.u32 %1, [%7+4], pol;\n"
+                        "@!p ld.global.nc.L2::cache_hint.u32 %2, [%7+8], pol;\n"
+                        "@!p ld.global.nc.L2::cache_hint.u32 %3, [%7+12], pol;\n"
+                        "@!p ld.global.nc.L2::cache_hint.u32 %4, [%7+16], pol;\n"
+                        "}\n"
+                        : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+                        : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
+                        : "memory");
+                } else
+#endif
                 asm volatile(
                     "{\n"
                     ".reg .pred p;\n"
@@ -384,6 +427,9 @@ struct Win : Chain<kSmemTable, kLib> {
                 }
                 const u32 kind = d & 7u, ev = (d >> 3) & 31u;
                 const u32 ins_all = insacc;
+#if SB200_PREFETCH && !defined(SB200_CPU_EMU)
+                if (t_next < lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + t_next));
+#endif
                 // ------------- commit the inserts of the path; the highest position wins (:191)
                 if (((ins_all >> lane) & 1u) && (mp & ins_all & ~((2u << lane) - 1u)) == 0u) this->tput(H, q);
                 __syncwarp();

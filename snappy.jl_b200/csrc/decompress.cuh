@@ -104,32 +104,40 @@ __device__ __forceinline__ void warp_copy_backref(u8* out, u64 op, u32 offset, u
 // reference's status for every input (first error in stream order).  Used for arbitrary streams
 // until the speculative parse has produced an index, and as the arbiter whenever the fast paths
 // see anything inconsistent.  `ip0` is the first byte after the varint header.
-__device__ __forceinline__ int decode_exact_warp(const u8* __restrict__ in, u64 L, u64 ip0,
-                                                 u8* __restrict__ out, u64 n, u32 lane,
-                                                 u64& produced) {
-    u64 ip = ip0, op = 0;
-    int status = ST_OK;
-    while (ip + 1 < L) {  // src/internal.jl:416
+// Range form: elements from *ip up to (not including) ip_stop, output position *op; returns the status of the first
+// failing element (ST_OK if none).  The whole-stream decoder is the range [ip0, L) from op = 0 plus the final length
+// check (src/Snappy.jl:50).
+__device__ __forceinline__ int decode_exact_range(const u8* __restrict__ in, u64 L, u64& ip, u64 ip_stop,
+                                                  u8* __restrict__ out, u64 n, u64& op, u32 lane) {
+    while (ip < ip_stop && ip + 1 < L) {  // src/internal.jl:416
         u32 c, tag4;
         load_tag(in, ip, L, c, tag4);
         ip += 1;
         Element e = decode_tag(c, tag4);
         ip += e.extra;
         if (e.is_copy) {
-            if (e.offset == 0 || (u64)e.offset > op) { status = ST_CORRUPT_COPY_OFFSET; break; }  // :499
-            if (n - op < e.len) { status = ST_CORRUPT_COPY_LENGTH; break; }                       // :505
+            if (e.offset == 0 || (u64)e.offset > op) return ST_CORRUPT_COPY_OFFSET;  // :499
+            if (n - op < e.len) return ST_CORRUPT_COPY_LENGTH;                       // :505
             warp_copy_backref(out, op, e.offset, e.len, lane);
             op += e.len;
         } else {
             // avail_in may be negative when the header bytes ran past the end (:517-518)
             long long avail_in = (long long)L - (long long)ip;
-            if (n - op < (u64)e.len || avail_in < (long long)e.len) { status = ST_CORRUPT_LITERAL; break; }
+            if (n - op < (u64)e.len || avail_in < (long long)e.len) return ST_CORRUPT_LITERAL;
             warp_copy_literal(out + op, in + ip, e.len, lane);
             op += e.len;
             ip += e.len;
         }
         __syncwarp();
     }
+    return ST_OK;
+}
+
+__device__ __forceinline__ int decode_exact_warp(const u8* __restrict__ in, u64 L, u64 ip0,
+                                                 u8* __restrict__ out, u64 n, u32 lane,
+                                                 u64& produced) {
+    u64 ip = ip0, op = 0;
+    int status = decode_exact_range(in, L, ip, L, out, n, op, lane);
     if (status == ST_OK && op != n) status = ST_INVALID_INPUT;  // src/Snappy.jl:50
     produced = op;
     return status;
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(kDecodeWarpsPerCta * 32, kMinBlocks * 4 / kDec
 k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, u32 nfrag, u32 first,
                    u32 count, u64 in_begin, u64 in_end, u8* __restrict__ out, u64 out_len,
                    DecodeResult* __restrict__ res, const DecodeDesc* __restrict__ descs = nullptr,
-                   u32 ndesc = 0) {
+                   u32 ndesc = 0, const u64* __restrict__ out_start = nullptr, u8* __restrict__ tile_flags = nullptr) {
     // fragments [first, first + count) of the nfrag the index describes (ranges let the host
     // overlap the device->host copy of finished output with the decoding of the rest)
     const u32 lane = lane_id();
@@ -358,14 +366,69 @@ k_decode_fragments(const u8* __restrict__ in, const u64* __restrict__ frag_off, 
     }
     const u64 ip = frag_off[f];
     const u64 ie = frag_off[f + 1];
-    const u64 ob = (u64)f * kBlockSize;
-    const u32 on = (u32)((out_len - ob < kBlockSize) ? (out_len - ob) : kBlockSize);
+    // out_start (index built by the parse for a foreign stream): tile f begins at the element that covers output
+    // byte f * 65536 -- a literal may straddle the boundary -- so tiles start where out_start says
+    const u64 ob = out_start ? out_start[f] : (u64)f * kBlockSize;
+    u64 oe = out_start ? out_start[f + 1] : ob + kBlockSize;
+    if (oe > out_len) oe = out_len;
+    const u32 on = (oe >= ob && oe - ob <= 0xffffffffull) ? (u32)(oe - ob) : 0u;
     bool ok = (ie >= ip) && (ie <= in_end) && (f != 0 || ip == in_begin) &&
-              (f != nfrag - 1 || ie == in_end);
+              (f != nfrag - 1 || ie == in_end) && (oe >= ob) && (ob <= out_len);
     if (ok) ok = decode_fast_warp(in, ip, ie, out + ob, on, lane);
     if (!ok && lane == 0) {
         atomicOr(&res->fallback, 1u);
         if (shard_flag) atomicOr(shard_flag, 1u);
+        if (tile_flags) tile_flags[f] = 1;
+    }
+}
+
+// Status arbiter, bounded: only the tiles the parallel decoder rejected (tile_flags) are decoded again, one warp,
+// element by element with the reference's checks (decode_exact_range), in stream order.  Every tile before the first
+// rejected one passed the (stricter) clean-tile validation, so its bytes are final and the reference accepts it too:
+// the first error this walk meets is the reference's first error.  A rejected tile that decodes fine in whole-stream
+// terms (a copy that reaches into an earlier tile) is simply complete afterwards.  The walk goes on through the
+// following tiles until it stands exactly on the start of a tile that was not rejected.
+__global__ void __launch_bounds__(32)
+k_decode_serial_tiles(const u8* __restrict__ in, u64 L, const u64* __restrict__ index,
+                      const u64* __restrict__ out_start, u32 nfrag, const u8* __restrict__ tile_flags,
+                      u8* __restrict__ out, u64 n, DecodeResult* __restrict__ res) {
+    const u32 lane = lane_id();
+    int status = ST_OK;
+    u64 ip = 0, op = 0;
+    bool ran_to_end = false;
+    u32 f = 0;
+    while (f < nfrag && status == ST_OK) {
+        if (!tile_flags[f]) {
+            f++;
+            continue;
+        }
+        // a known start: this tile's own index entry, else the nearest earlier one (tile 0 starts behind the header)
+        u32 s = f;
+        while (s > 0 && index[s] >= L) s--;
+        ip = index[s];
+        op = out_start ? out_start[s] : (u64)s * kBlockSize;
+        u32 cur = s;
+        for (;;) {
+            // one element at a time, so that the walk can stop on a tile start
+            u64 stop = ip + 1;
+            status = decode_exact_range(in, L, ip, stop, out, n, op, lane);
+            if (status != ST_OK) break;
+            if (ip + 1 >= L) {  // end of the stream (a lone trailing byte is ignored, src/internal.jl:416)
+                ran_to_end = true;
+                break;
+            }
+            while (cur + 1 < nfrag && op >= (out_start ? out_start[cur + 1] : (u64)(cur + 1) * kBlockSize)) cur++;
+            const u64 ts = out_start ? out_start[cur] : (u64)cur * kBlockSize;
+            if (cur > f && op == ts && ip == index[cur] && !tile_flags[cur]) break;  // back on a good tile
+        }
+        if (ran_to_end || status != ST_OK) break;
+        f = cur;
+    }
+    if (status == ST_OK && ran_to_end && op != n) status = ST_INVALID_INPUT;  // src/Snappy.jl:50
+    if (lane == 0) {
+        res->status = status;
+        res->produced = op;
+        res->err_op = op;
     }
 }
 

@@ -46,7 +46,7 @@ constexpr u32 kBridgeBudget = 20000;  // elements a bridge may walk before it gi
 constexpr u64 kDeadPos = ~0ull;
 constexpr u32 kNextDead = 0xffffffffu;  // chain cannot be followed from here
 
-enum : u32 { PF_ANOMALY = 1u, PF_NOT_CLEAN = 2u, PF_BROKEN = 4u };
+enum : u32 { PF_ANOMALY = 1u, PF_NOT_CLEAN = 2u, PF_BROKEN = 4u, PF_STRADDLE = 8u };
 
 struct ParseArrays {
     u64* first;         // [nchunk]
@@ -214,11 +214,18 @@ k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
     pa.outb[k] = (u32)produced;
 }
 
-// Walk each real chunk again with its output offset known; record the compressed position of every
-// element that starts exactly on a 64 KiB output boundary; flag anything not fragment-clean.
+// Walk each real chunk again with its output offset known and record where every TILE of the output begins: tile k
+// starts at the element that covers output byte k * 65536 (index[k] = its position in the stream, out_start[k] = its
+// output offset).  Everything Snappy.jl, libsnappy and Google snappy emit starts a new element exactly on every
+// 64 KiB boundary (they compress 64 KiB blocks independently), so out_start[k] == k * 65536 there.  `relaxed`: a
+// LITERAL may straddle a boundary (streams of encoders that merge the literals of neighbouring blocks, e.g.
+// tests/data/alice29.snappy); the tile then begins a few bytes early, at that literal.  A copy that straddles, or one
+// that reaches back over the boundary of its tile, makes the tile depend on earlier output: flagged PF_NOT_CLEAN (the
+// indexed decoder rejects such a tile anyway and the bounded serial walk decides).
 __global__ void __launch_bounds__(kParseThreads)
 k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
-              const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag, u64 E, u64 out_base, u32 pshift) {
+              const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag, u64 E, u64 out_base, u32 pshift,
+              u64* __restrict__ out_start = nullptr, u32 relaxed = 0) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     if (k == 0 && E >= L) index[nfrag] = L;
@@ -227,18 +234,51 @@ k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
     u64 start, end;
     chunk_range(hdr, E, k, pshift, start, end);
     u64 op = out_base + out_off[k];  // out_base: output bytes of the segments before this one
-    bool clean = true;
+    bool clean = true, straddle = false;
     Element e;
     while (ip < end && ip + 1 < L) {
         const u64 at = ip;
         if (!walk_step(in, L, ip, e)) { clean = false; break; }
         const u32 in_frag = (u32)(op & (kBlockSize - 1));
-        if (in_frag == 0 && (op >> 16) < nfrag) index[op >> 16] = at;
-        if (in_frag + (u64)e.len > kBlockSize) clean = false;
+        if (in_frag == 0) {
+            if ((op >> 16) < nfrag) {
+                index[op >> 16] = at;
+                if (out_start) out_start[op >> 16] = op;
+            }
+            if ((u64)e.len > kBlockSize) {  // a literal longer than a tile: the tiles it swallows are empty
+                if (relaxed && out_start && !e.is_copy) {
+                    straddle = true;
+                    for (u64 t = (op >> 16) + 1; (t << 16) < op + e.len && t < nfrag; t++) {
+                        index[t] = at;
+                        out_start[t] = op;
+                    }
+                } else {
+                    clean = false;
+                }
+            }
+        } else if (in_frag + (u64)e.len > kBlockSize) {  // the element straddles (at least) one boundary
+            if (relaxed && out_start && !e.is_copy) {
+                straddle = true;
+                for (u64 t = (op >> 16) + 1; (t << 16) < op + e.len && t < nfrag; t++) {
+                    index[t] = at;
+                    out_start[t] = op;
+                }
+            } else {
+                clean = false;
+            }
+        }
         if (e.is_copy && e.offset > in_frag) clean = false;
         op += e.len;
     }
     if (!clean) atomicOr(&pa.counters[0], PF_NOT_CLEAN);
+    if (straddle) atomicOr(&pa.counters[0], PF_STRADDLE);
+}
+
+// first tile whose index entry was never written (the chain broke before it): everything below is trustworthy
+__global__ void __launch_bounds__(256)
+k_first_missing(const u64* __restrict__ index, u32 nfrag, u64 L, u32* __restrict__ first) {
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i <= nfrag && index[i] > L) atomicMin(first, i);
 }
 
 // flags, segment exit and output bytes straight into pinned host memory: a device-to-host copy would

@@ -113,7 +113,7 @@ struct Context {
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for decode
-    DevBuf result, parse_a, parse_b, parse_c, index;
+    DevBuf result, parse_a, parse_b, parse_c, index, index_out, tile_flags;
     // staging for the host-buffer API
     DevBuf stage_in, stage_out;
     void* pinned = nullptr;  // small pinned readback area (kPinnedBytes)
@@ -122,6 +122,7 @@ struct Context {
     float last_ms[2] = {0.f, 0.f};
     int last_launches[2] = {0, 0};
     bool ev_pending[2] = {false, false};
+    int last_path = 0;  // how the last uncompress decoded: 0 side index, 1 parse + tiles, 2 ... + bounded serial walk, 3 whole-stream serial
     Options& opt = g_opt;
 };
 
@@ -372,7 +373,7 @@ void ctx_destroy(Context& c) {
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
     for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a,
-                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order, &c.trace})
+                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order, &c.trace, &c.index_out, &c.tile_flags})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
     if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
@@ -786,7 +787,8 @@ int decode_exact_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_
 // pipe_chunk_frags fragments, each followed by its device-to-host copy on the copy stream (*ri counts
 // the events used).  No synchronisation.
 int decode_launch(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed, const u64* d_index,
-                  cudaStream_t st, u32 fa, u32 fb, u8* host_out, int* ri, u32 range = 0) {
+                  cudaStream_t st, u32 fa, u32 fb, u8* host_out, int* ri, u32 range = 0,
+                  const u64* out_start = nullptr, u8* tile_flags = nullptr) {
     const u32 nfrag = frag_count(claimed);
     DecodeResult* res = (DecodeResult*)c.result.p;
     const bool ranged = host_out != nullptr;
@@ -796,13 +798,16 @@ int decode_launch(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u
         const u32 grid = (cnt + kDecodeWarpsPerCta - 1) / kDecodeWarpsPerCta;
         if (c.opt.decode_occupancy == 12)
             k_decode_fragments<12><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
-                                                                             (u64)n, d_out, (u64)claimed, res);
+                                                                             (u64)n, d_out, (u64)claimed, res, nullptr,
+                                                                             0u, out_start, tile_flags);
         else if (c.opt.decode_occupancy == 10)
             k_decode_fragments<10><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
-                                                                             (u64)n, d_out, (u64)claimed, res);
+                                                                             (u64)n, d_out, (u64)claimed, res, nullptr,
+                                                                             0u, out_start, tile_flags);
         else
             k_decode_fragments<8><<<grid, kDecodeWarpsPerCta * 32, 0, st>>>(d_in, d_index, nfrag, f0, cnt, (u64)hdr,
-                                                                            (u64)n, d_out, (u64)claimed, res);
+                                                                            (u64)n, d_out, (u64)claimed, res, nullptr,
+                                                                            0u, out_start, tile_flags);
         c.last_launches[1] += 1;
         if (ranged) {
             if (*ri >= kMaxPipeChunks) return fail_cuda(cudaErrorInvalidValue, "decode_launch: too many ranges");
@@ -861,7 +866,8 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
 // ready, -1 when the stream is not fragment-clean or shows any anomaly (the exact serial decoder then
 // decides), or a CUDA error status (> 0).
 int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t E, u64 out_base, u32 nfrag,
-                        cudaStream_t st, u64* seg_exit, u64* seg_out) {
+                        cudaStream_t st, u64* seg_exit, u64* seg_out, u64* out_start = nullptr,
+                        u64* flags_out = nullptr) {
     if (nfrag == 0 || E <= hdr) return -1;
     const u64 body = E - hdr;
     const u32 pshift = (u32)c.opt.parse_chunk_log2;
@@ -902,7 +908,7 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
     k_parse_final<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
     k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
     k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off, (u64*)c.index.p, nfrag,
-                                                  (u64)E, out_base, pshift);
+                                                  (u64)E, out_base, pshift, out_start, out_start ? 1u : 0u);
     c.last_launches[1] += 6;
     CU(cudaGetLastError());
     volatile u64* h3 = (volatile u64*)h;
@@ -913,9 +919,13 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
     if (getenv("SNAPPY_B200_DEBUG"))
         fprintf(stderr, "[snappy_b200] parse [%zu, %zu): nchunk=%u flags=%u out=%llu exit=%llu\n", hdr, E, nchunk,
                 (unsigned)flags, (unsigned long long)total, (unsigned long long)ex);
-    if (flags != 0) return -1;
     *seg_exit = ex;
     *seg_out = total;
+    if (flags_out) {  // relaxed whole-stream mode: the caller decides what the flags mean
+        *flags_out = flags;
+        return 0;
+    }
+    if (flags != 0) return -1;
     return 0;
 }
 
@@ -927,6 +937,80 @@ int build_index_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u32 cla
     const int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total);
     if (rc != 0) return rc;
     return total == claimed ? 0 : -1;
+}
+
+// Arbitrary stream, no usable side index.  The parse builds the tile index (relaxed: a literal may straddle a 64 KiB
+// boundary); the indexed decoder runs over every tile whose both ends are known and marks the tiles it rejects; the
+// bounded serial walk (k_decode_serial_tiles) then decodes only those, and everything behind the point where the
+// parse lost the chain, with the reference's checks.  So a corrupt 1 GiB stream costs the parallel decode of its good
+// prefix plus one tile of serial work, and the status is the reference's.  Returns a status (>= 0), or -1: nothing
+// usable came out of the parse (caller: whole-stream serial decoder).
+int decode_parsed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u32 claimed, cudaStream_t st,
+                         u8* host_out, bool* host_copied) {
+    const u32 nfrag = frag_count(claimed);
+    if (nfrag == 0 || n <= hdr) return -1;
+    CU(c.index.ensure(((size_t)nfrag + 1) * 8));
+    CU(c.index_out.ensure(((size_t)nfrag + 1) * 8));
+    CU(c.tile_flags.ensure((size_t)nfrag + 64));
+    u64* idx = (u64*)c.index.p;
+    u64* ost = (u64*)c.index_out.p;
+    u8* tf = (u8*)c.tile_flags.p;
+    CU(cudaMemsetAsync(idx, 0xff, ((size_t)nfrag + 1) * 8, st));
+    CU(cudaMemsetAsync(ost, 0xff, ((size_t)nfrag + 1) * 8, st));
+    CU(cudaMemsetAsync(tf, 0, (size_t)nfrag + 64, st));
+    u64* hseed = (u64*)((u8*)c.pinned + 3072);  // tile 0 starts behind the header whatever the parse finds
+    hseed[0] = hdr;
+    hseed[1] = 0;
+    hseed[2] = claimed;
+    CU(cudaMemcpyAsync(idx, hseed, 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ost, hseed + 1, 8, cudaMemcpyHostToDevice, st));
+    u64 ex = 0, total = 0, pflags = 0;
+    int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total, ost, &pflags);
+    if (rc != 0) return rc;
+    CU(cudaMemcpyAsync(ost + nfrag, hseed + 2, 8, cudaMemcpyHostToDevice, st));
+    const bool complete = !(pflags & (PF_ANOMALY | PF_BROKEN)) && total == claimed;
+    u32 tvalid = nfrag;  // tiles [0, tvalid) have both ends in the index
+    if (!complete) {
+        u32* d_first = (u32*)((u8*)c.result.p + 128);
+        u32* h_first = (u32*)((u8*)c.pinned + 3104);
+        *h_first = nfrag + 1;
+        CU(cudaMemcpyAsync(d_first, h_first, 4, cudaMemcpyHostToDevice, st));
+        k_first_missing<<<(nfrag + 1 + 255) / 256, 256, 0, st>>>(idx, nfrag, (u64)n, d_first);
+        CU(cudaMemcpyAsync(h_first, d_first, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const u32 first = *h_first;  // index[first] was never written (<= nfrag when the chain broke)
+        tvalid = first == 0 ? 0u : (first > nfrag ? nfrag : first - 1);
+        if (first <= nfrag && first > 0 && tvalid > 0) tvalid = first - 1;
+    }
+    CU(cudaMemsetAsync(c.result.p, 0, sizeof(DecodeResult), st));
+    if (c.opt.timing) CU(cudaEventRecord(c.ev[2], st));
+    // host-buffer API: ranged device-to-host copies only when the tiles are the aligned 64 KiB fragments
+    const bool ranged = host_out && pflags == 0 && complete && c.opt.host_pipeline && nfrag > (u32)c.opt.pipe_chunk_frags;
+    int ri = 0;
+    if (tvalid) {
+        rc = decode_launch(c, d_in, n, hdr, d_out, claimed, idx, st, 0, tvalid, ranged ? host_out : nullptr, &ri, 0, ost, tf);
+        if (rc != SNAPPY_B200_OK) return rc;
+    }
+    rc = decode_finish(c, st, ranged);
+    if (rc > 0) return rc;
+    if (rc == 0 && complete) {
+        if (ranged && host_copied) *host_copied = true;
+        c.last_path = 1;
+        return SNAPPY_B200_OK;
+    }
+    c.last_path = 2;
+    // some tiles were rejected, or the index ends early: the bounded serial walk decides
+    if (tvalid < nfrag) CU(cudaMemsetAsync(tf + tvalid, 1, nfrag - tvalid, st));
+    if (!complete) CU(cudaMemsetAsync(tf + nfrag - 1, 1, 1, st));  // the walk must see the end of the stream (length check)
+    DecodeResult* res = (DecodeResult*)c.result.p;
+    k_decode_serial_tiles<<<1, 32, 0, st>>>(d_in, (u64)n, idx, ost, nfrag, tf, d_out, (u64)claimed, res);
+    c.last_launches[1] += 1;
+    CU(cudaGetLastError());
+    DecodeResult* h = (DecodeResult*)((u8*)c.pinned + 128);
+    CU(cudaMemcpyAsync(h, res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (host_copied) *host_copied = false;  // ranges that went down early may hold bytes of rejected tiles
+    return h->status;
 }
 
 int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, size_t out_cap,
@@ -947,19 +1031,16 @@ int uncompress_device_locked(Context& c, const u8* d_in, size_t n, u8* d_out, si
     if (out_cap < claimed) return SNAPPY_B200_BUFFER_TOO_SMALL;
     *out_len = claimed;
     if (c.opt.decode_variant != 1) {
-        if (d_index) {
+        if (d_index) {  // a wrong index cannot change the result: any rejected fragment sends us to the parse
+            c.last_path = 0;
             rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, d_index, st, host_out, host_copied);
             if (rc >= 0) return rc;
+            if (host_copied) *host_copied = false;
         }
-        // arbitrary stream: segmented speculative parse builds the index on the device
-        rc = build_index_locked(c, d_in, n, hdr, claimed, st);
-        if (rc > 0) return rc;
-        if (rc == 0) {
-            rc = decode_indexed_locked(c, d_in, n, hdr, d_out, claimed, (const u64*)c.index.p, st, host_out,
-                                       host_copied);
-            if (rc >= 0) return rc;
-        }
+        rc = decode_parsed_locked(c, d_in, n, hdr, d_out, claimed, st, host_out, host_copied);
+        if (rc >= 0) return rc;
     }
+    c.last_path = 3;
     return decode_exact_locked(c, d_in, n, hdr, d_out, claimed, st);
 }
 
@@ -1847,6 +1928,7 @@ int snappy_b200_get_option(const char* name) {
     parse_env_options();
     std::unique_lock<std::mutex> lk(g_opt_mu);
     const Options& o = g_opt;
+    if (!strcmp(name, "last_decode_path")) return tl_last ? tl_last->last_path : -1;
     if (!strcmp(name, "experiments")) {
 #ifdef SB200_EXPERIMENTS
         return 1;

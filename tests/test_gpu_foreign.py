@@ -1,0 +1,112 @@
+"""GPU: streams this library did not write and corrupt streams at size.
+
+The index-free path: the parse builds a tile index (a literal may straddle a 64 KiB output boundary: the tile then
+starts at that literal), the indexed decoder runs over all tiles and marks the ones it rejects, and a bounded serial
+walk decodes only those with the reference's checks.  `last_decode_path`: 0 side index, 1 parse + tiles, 2 parse + tiles
++ bounded serial walk, 3 whole-stream serial decoder."""
+import time
+
+import numpy as np
+import pytest
+
+from conftest import read_data
+
+pytestmark = pytest.mark.gpu
+FRAGMENT = 65536
+
+
+def _path(snappy):
+    return snappy._abi.lib().snappy_b200_get_option(b"last_decode_path")
+
+
+def test_alice29_snappy_takes_the_parallel_path(snappy, oracle):
+    """tests/data/alice29.snappy (a 32 KiB-block encoder's stream whose literals straddle the block boundaries;
+    test/runtests.jl decodes it): tiles start at the straddling literals, no serial decoding at all"""
+    import torch
+    from snappy_jl_b200 import device
+    data = read_data("alice29.snappy")
+    want = read_data("alice29.txt")
+    got = device.uncompress_device(torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda())
+    assert got.cpu().numpy().tobytes() == want
+    assert _path(snappy) == 1
+    assert snappy.uncompress(data) == want   # host-buffer API, same path
+
+
+def _blocky_stream(oracle, raw, block):
+    """every `block` bytes compressed on their own (copies never leave their block), concatenated behind one header:
+    a valid stream whose elements straddle the 64 KiB boundaries wherever the block size does not divide 65536"""
+    parts = [oracle.encode32(raw.size)]
+    for o in range(0, raw.size, block):
+        s = oracle.compress(raw[o: o + block].tobytes())
+        _, k = oracle.parse32(s, 0)
+        parts.append(s[k:])
+    return b"".join(parts)
+
+
+@pytest.mark.parametrize("block", [32768, 50000, 65536, 7777])
+def test_block_structured_foreign_streams(snappy, oracle, block):
+    import torch
+    from snappy_jl_b200 import device, synth
+    raw = synth.mix(48, seed=17, tail=4321)
+    stream = _blocky_stream(oracle, raw, block)
+    assert oracle.uncompress_np(stream).tobytes() == raw.tobytes()
+    got = device.uncompress_device(torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).cuda())
+    assert np.array_equal(got.cpu().numpy(), raw)
+    # blocks that tile the 64 KiB boundaries decode fully in parallel; the others need the bounded serial walk for
+    # the tiles a copy reaches out of -- but never the whole-stream serial decoder
+    assert _path(snappy) == (1 if 65536 % block == 0 else 2)
+
+
+def test_corrupt_256_mib_stream_is_rejected_fast_with_the_reference_status(snappy, oracle):
+    """one garbled spot in the middle of a 256 MiB stream: the reference's status, and the cost of the good prefix in
+    parallel plus one tile of serial work -- not a serial pass over the stream"""
+    import torch
+    from snappy_jl_b200 import device, synth
+    tile = synth.mix(512, seed=23)                    # 32 MiB
+    reps = 8
+    total = tile.size * reps
+    parts, sizes = oracle.compress_fragments(tile, total, 0, 512)
+    hdr = np.frombuffer(oracle.encode32(total), dtype=np.uint8)
+    good = np.concatenate([hdr] + [parts] * reps)
+    raw = np.tile(tile, reps)
+    bad = good.copy()
+    pos = good.size // 2 + 12345
+    bad[pos: pos + 24] ^= 0xA7
+    want_status = oracle.status_of_uncompress(bad)
+    assert want_status != 0
+    d_bad = torch.from_numpy(bad).cuda()
+    d_good = torch.from_numpy(good).cuda()
+    out = torch.empty(total, dtype=torch.uint8, device="cuda")
+    device.uncompress_device(d_good, out=out, claimed=total)          # warm-up, and the good stream still decodes
+    assert torch.equal(out, torch.from_numpy(raw).cuda()) and _path(snappy) == 1
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with pytest.raises(snappy.SnappyError) as e:
+        device.uncompress_device(d_bad, out=out, claimed=total)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert e.value.status == want_status
+    assert _path(snappy) == 2
+    assert dt < 0.1, "rejecting the corrupt stream took %.1f ms" % (dt * 1e3)
+    # a truncated stream, and one whose header lies about the length
+    for s in (good[: good.size // 3], np.concatenate([np.frombuffer(oracle.encode32(total - 5), dtype=np.uint8), good[hdr.size:]])):
+        want = oracle.status_of_uncompress(s)
+        assert want != 0
+        with pytest.raises(snappy.SnappyError) as e:
+            device.uncompress_device(torch.from_numpy(np.ascontiguousarray(s)).cuda())
+        assert e.value.status == want
+
+
+def test_wrong_side_index_cannot_change_the_result(snappy, oracle):
+    import torch
+    from snappy_jl_b200 import device, synth
+    raw = synth.mix(20, seed=3, tail=100)
+    d = torch.from_numpy(raw).cuda()
+    stream, index = device.compress_device(d, want_index=True)
+    bogus = index.clone()
+    bogus[5] += 3
+    bogus[11] = 0
+    back = device.uncompress_device(stream, index=bogus, claimed=raw.size)
+    assert torch.equal(back, d) and _path(snappy) == 1
+    back = device.uncompress_device(stream, index=index, claimed=raw.size)
+    assert torch.equal(back, d) and _path(snappy) == 0
