@@ -225,7 +225,7 @@ k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
 __global__ void __launch_bounds__(kParseThreads)
 k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa,
               const u64* __restrict__ out_off, u64* __restrict__ index, u32 nfrag, u64 E, u64 out_base, u32 pshift,
-              u64* __restrict__ out_start = nullptr, u32 relaxed = 0) {
+              u64* __restrict__ out_start = nullptr, u32 relaxed = 0, u64 out_total = 0) {
     const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
     if (k >= nchunk) return;
     if (k == 0 && E >= L) index[nfrag] = L;
@@ -268,6 +268,24 @@ k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
             }
         }
         if (e.is_copy && e.offset > in_frag) clean = false;
+        if (relaxed) {
+            // The reference's per-element checks depend on the element header and the output position only, never on
+            // decoded bytes: offset == 0 or beyond what is produced (src/internal.jl:499), more bytes than the claimed
+            // length leaves room for (:505, :518).  So the status of a corrupt stream falls out of the parse: the
+            // failing element with the smallest stream position wins (the reference stops at the first one).
+            u32 err = 0;
+            const u64 room = out_total >= op ? out_total - op : 0;
+            if (e.is_copy) {
+                if (e.offset == 0 || (u64)e.offset > op) err = ST_CORRUPT_COPY_OFFSET;
+                else if (room < e.len) err = ST_CORRUPT_COPY_LENGTH;
+            } else if (room < (u64)e.len) {
+                err = ST_CORRUPT_LITERAL;
+            }
+            if (err) {
+                atomicMin(reinterpret_cast<unsigned long long*>(pa.counters) + 2, (unsigned long long)((at << 3) | err));
+                break;  // nothing behind the first failing element of this chunk matters
+            }
+        }
         op += e.len;
     }
     if (!clean) atomicOr(&pa.counters[0], PF_NOT_CLEAN);
@@ -287,6 +305,7 @@ __global__ void k_parse_report(const u32* __restrict__ counters, const u64* __re
     host3[0] = counters[0];
     host3[1] = reinterpret_cast<const u64*>(counters)[1];
     host3[2] = *total;
+    host3[3] = reinterpret_cast<const u64*>(counters)[2];  // (stream position << 3) | status of the first failing element
     __threadfence_system();
 }
 

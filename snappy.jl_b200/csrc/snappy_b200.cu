@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -30,6 +32,8 @@
 using namespace sb200;
 
 namespace {
+
+struct Bounce;  // pinned slots for pageable host buffers (defined with the host-buffer paths below)
 
 thread_local std::string g_last_error;
 
@@ -118,6 +122,12 @@ struct Context {
     DevBuf stage_in, stage_out;
     void* pinned = nullptr;  // small pinned readback area (kPinnedBytes)
     void* pinned_zero = nullptr;  // kTailPad zero bytes (pinned): pads go up through the copy engine
+    Bounce* bounce = nullptr;         // pinned slots for pageable host buffers
+    struct DownRange {
+        size_t off, len;
+        int ev;
+    };
+    std::vector<DownRange>* defer_down = nullptr;  // decode_launch: list the finished ranges instead of copying them
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[2] = {0.f, 0.f};
     int last_launches[2] = {0, 0};
@@ -298,6 +308,7 @@ void parse_env_options() {
 }
 
 void ctx_destroy(Context& c);
+void bounce_destroy(Context& c);
 
 // Create the streams, events and pinned areas of a lane (current device == `device`); slot.mu is held.
 int ctx_init(Context& c, int device, DeviceSlot& slot) {
@@ -378,6 +389,7 @@ void ctx_destroy(Context& c) {
     if (c.pinned) cudaFreeHost(c.pinned);
     if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
     c.pinned = c.pinned_zero = nullptr;
+    bounce_destroy(c);
     for (auto& ev : c.ev) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
@@ -815,8 +827,12 @@ int decode_launch(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d_out, u
             const size_t ol = ((size_t)claimed - ob < (size_t)cnt * kBlockSize) ? ((size_t)claimed - ob)
                                                                                  : (size_t)cnt * kBlockSize;
             CU(cudaEventRecord(c.ev_done[*ri], st));
-            CU(cudaStreamWaitEvent(c.s_d2h, c.ev_done[*ri], 0));
-            CU(cudaMemcpyAsync(host_out + ob, d_out + ob, ol, cudaMemcpyDeviceToHost, c.s_d2h));
+            if (c.defer_down) {  // pageable destination: the caller drains the range through the bounce slots
+                c.defer_down->push_back(Context::DownRange{ob, ol, *ri});
+            } else {
+                CU(cudaStreamWaitEvent(c.s_d2h, c.ev_done[*ri], 0));
+                CU(cudaMemcpyAsync(host_out + ob, d_out + ob, ol, cudaMemcpyDeviceToHost, c.s_d2h));
+            }
             *ri += 1;
         }
     }
@@ -867,7 +883,7 @@ int decode_indexed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* 
 // decides), or a CUDA error status (> 0).
 int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t E, u64 out_base, u32 nfrag,
                         cudaStream_t st, u64* seg_exit, u64* seg_out, u64* out_start = nullptr,
-                        u64* flags_out = nullptr) {
+                        u64* flags_out = nullptr, u64 out_total = 0, u64* first_err = nullptr) {
     if (nfrag == 0 || E <= hdr) return -1;
     const u64 body = E - hdr;
     const u32 pshift = (u32)c.opt.parse_chunk_log2;
@@ -883,6 +899,7 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
     u32* h = (u32*)((u8*)c.pinned + 1024);
 
     CU(cudaMemsetAsync(pa.counters, 0, 64, st));
+    CU(cudaMemsetAsync((u8*)pa.counters + 16, 0xff, 8, st));  // first failing element: none yet
     const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
     const u32 lgrid = (nchunk + 255) / 256;
     k_parse_guess<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
@@ -908,7 +925,7 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
     k_parse_final<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, (u64)E, pshift);
     k_scan_sizes<<<1, 1024, 0, st>>>(pa.outb, nchunk, 0, out_off);
     k_build_index<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off, (u64*)c.index.p, nfrag,
-                                                  (u64)E, out_base, pshift, out_start, out_start ? 1u : 0u);
+                                                  (u64)E, out_base, pshift, out_start, out_start ? 1u : 0u, out_total);
     c.last_launches[1] += 6;
     CU(cudaGetLastError());
     volatile u64* h3 = (volatile u64*)h;
@@ -921,6 +938,7 @@ int build_index_segment(Context& c, const u8* d_in, size_t n, size_t hdr, size_t
                 (unsigned)flags, (unsigned long long)total, (unsigned long long)ex);
     *seg_exit = ex;
     *seg_out = total;
+    if (first_err) *first_err = h3[3];
     if (flags_out) {  // relaxed whole-stream mode: the caller decides what the flags mean
         *flags_out = flags;
         return 0;
@@ -964,9 +982,19 @@ int decode_parsed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d
     hseed[2] = claimed;
     CU(cudaMemcpyAsync(idx, hseed, 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ost, hseed + 1, 8, cudaMemcpyHostToDevice, st));
-    u64 ex = 0, total = 0, pflags = 0;
-    int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total, ost, &pflags);
+    u64 ex = 0, total = 0, pflags = 0, first_err = ~0ull;
+    int rc = build_index_segment(c, d_in, n, hdr, n, 0, nfrag, st, &ex, &total, ost, &pflags, (u64)claimed, &first_err);
     if (rc != 0) return rc;
+    if (first_err != ~0ull) {
+        // an element the reference rejects, found by the parse (header + output position decide, not data): its
+        // status, at once -- the reference stops there too and hands out nothing
+        c.last_path = 1;
+        return (int)(first_err & 7);
+    }
+    if (!(pflags & (PF_ANOMALY | PF_BROKEN)) && total != claimed) {
+        c.last_path = 1;
+        return SNAPPY_B200_INVALID_INPUT;  // every element is fine, the lengths do not add up (src/Snappy.jl:50)
+    }
     CU(cudaMemcpyAsync(ost + nfrag, hseed + 2, 8, cudaMemcpyHostToDevice, st));
     const bool complete = !(pflags & (PF_ANOMALY | PF_BROKEN)) && total == claimed;
     u32 tvalid = nfrag;  // tiles [0, tvalid) have both ends in the index
@@ -1224,6 +1252,262 @@ int snappy_b200_uncompress_device(const uint8_t* d_in, size_t n, uint8_t* d_out,
                                     (cudaStream_t)stream);
 }
 
+extern "C++" {
+namespace {
+
+// ---- pageable host buffers (what the reference API hands over: src/Snappy.jl:25,48 allocate plain Vector{UInt8}) ----
+// A cudaMemcpyAsync from pageable memory is a synchronous, single-threaded staging copy inside the driver (~5 GB/s
+// measured through this library's streamed paths: 236 ms per GiB round trip against 49 ms from pinned buffers).  So
+// the streamed paths bounce pageable buffers through a small ring of pinned slots themselves:
+//   up   : every piece is [host function: parallel memcpy user -> slot][copy slot -> device], enqueued UP FRONT on
+//          two alternating streams (the memcpy of piece k+1 overlaps the DMA of piece k); being ordinary stream work
+//          it keeps the rule of the streamed compress path that everything a persistent kernel waits for is queued
+//          before that kernel;
+//   down : [copy device -> slot] a few pieces ahead, then parallel memcpy slot -> user on the calling thread.
+class CopyPool {  // a few persistent threads that split one memcpy among themselves (and the caller)
+   public:
+    static CopyPool& get() {
+        static CopyPool p;
+        return p;
+    }
+    void copy(void* dst, const void* src, size_t n) {
+        if (n < (4u << 20) || th_.empty()) {
+            memcpy(dst, src, n);
+            return;
+        }
+        std::unique_lock<std::mutex> one(job_mu_);  // one job at a time: the memory system is the limit anyway
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            dst_ = (u8*)dst;
+            src_ = (const u8*)src;
+            n_ = n;
+            next_.store(0);
+            pending_ = (int)th_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+   private:
+    static constexpr size_t kBlock = 1u << 20;
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int t = hw >= 16 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+        if (const char* e = getenv("SNAPPY_B200_COPY_THREADS")) t = atoi(e) - 1;
+        for (int i = 0; i < t; i++) th_.emplace_back([this] { loop(); });
+        for (auto& x : th_) x.detach();  // they sleep on the condition variable for the life of the process
+    }
+    void work() {
+        for (;;) {
+            const size_t o = next_.fetch_add(kBlock);
+            if (o >= n_) break;
+            memcpy(dst_ + o, src_ + o, n_ - o < kBlock ? n_ - o : kBlock);
+        }
+    }
+    void loop() {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            work();
+            std::unique_lock<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    u8* dst_ = nullptr;
+    const u8* src_ = nullptr;
+    size_t n_ = 0;
+    std::atomic<size_t> next_{0};
+    int pending_ = 0;
+    unsigned long gen_ = 0;
+};
+
+constexpr size_t kBounceSlot = 16u << 20;  // bytes per pinned slot
+constexpr int kBounceUp = 4, kBounceDown = 4;
+
+struct Bounce {  // per lane, created on the first pageable call
+    u8* pin = nullptr;  // (kBounceUp + kBounceDown) slots
+    cudaStream_t s_up[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
+    cudaEvent_t ev_down[kBounceDown] = {};
+};
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+struct UpJob {
+    void* dst;
+    const void* src;
+    size_t n;
+};
+void CUDART_CB up_job_fn(void* p) {
+    UpJob* j = (UpJob*)p;
+    CopyPool::get().copy(j->dst, j->src, j->n);
+}
+
+int bounce_init(Context& c) {
+    if (c.bounce) return SNAPPY_B200_OK;
+    Bounce* b = new Bounce();
+    cudaError_t e = cudaMallocHost((void**)&b->pin, (size_t)(kBounceUp + kBounceDown) * kBounceSlot);
+    if (e != cudaSuccess) {
+        delete b;
+        return fail_cuda(e, "cudaMallocHost (bounce slots)");
+    }
+    c.bounce = b;
+    for (int i = 0; i < 2; i++) {
+        CU(cudaStreamCreateWithFlags(&b->s_up[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&b->ev_up[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kBounceDown; i++) CU(cudaEventCreateWithFlags(&b->ev_down[i], cudaEventDisableTiming));
+    return SNAPPY_B200_OK;
+}
+
+void bounce_destroy(Context& c) {
+    Bounce* b = c.bounce;
+    if (!b) return;
+    for (int i = 0; i < 2; i++) {
+        if (b->s_up[i]) cudaStreamDestroy(b->s_up[i]);
+        if (b->ev_up[i]) cudaEventDestroy(b->ev_up[i]);
+    }
+    for (int i = 0; i < kBounceDown; i++)
+        if (b->ev_down[i]) cudaEventDestroy(b->ev_down[i]);
+    if (b->pin) cudaFreeHost(b->pin);
+    delete b;
+    c.bounce = nullptr;
+}
+
+// Host -> device.  Pinned source: one copy on c.s_h2d.  Pageable source: pieces through the pinned slots, all
+// enqueued now (see above).  after(stream) is where the caller queues what must follow everything put so far
+// (a ready count, an event): it first makes `stream` wait for the other upload stream.
+struct Uploader {
+    Context& c;
+    bool pageable;
+    std::vector<UpJob> jobs;  // reserved up front: the host functions hold pointers into it
+    int piece = 0;
+    cudaStream_t last = nullptr;
+    Uploader(Context& ctx, bool pg, size_t total_bytes, int extra) : c(ctx), pageable(pg) {
+        if (pageable) jobs.reserve(total_bytes / kBounceSlot + (size_t)extra + 8);
+        last = c.s_h2d;
+    }
+    int begin(cudaEvent_t after_this) {  // the upload streams start behind `after_this` (recorded by the caller)
+        if (!pageable) return SNAPPY_B200_OK;
+        for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(c.bounce->s_up[i], after_this, 0));
+        return SNAPPY_B200_OK;
+    }
+    int put(u8* d_dst, const u8* h_src, size_t len) {
+        if (!pageable) {
+            if (len) CU(cudaMemcpyAsync(d_dst, h_src, len, cudaMemcpyHostToDevice, c.s_h2d));
+            last = c.s_h2d;
+            return SNAPPY_B200_OK;
+        }
+        Bounce& b = *c.bounce;
+        for (size_t o = 0; o < len; o += kBounceSlot) {
+            const size_t l = len - o < kBounceSlot ? len - o : kBounceSlot;
+            const int par = piece & 1;
+            u8* slot = b.pin + (size_t)(piece % kBounceUp) * kBounceSlot;
+            if (jobs.size() == jobs.capacity()) return fail_cuda(cudaErrorInvalidValue, "upload: piece list full");
+            jobs.push_back(UpJob{slot, h_src + o, l});
+            CU(cudaLaunchHostFunc(b.s_up[par], up_job_fn, &jobs.back()));
+            CU(cudaMemcpyAsync(d_dst + o, slot, l, cudaMemcpyHostToDevice, b.s_up[par]));
+            CU(cudaEventRecord(b.ev_up[par], b.s_up[par]));
+            last = b.s_up[par];
+            piece++;
+        }
+        return SNAPPY_B200_OK;
+    }
+    int after(cudaStream_t* st) {
+        *st = last;
+        if (pageable && piece > 0) {
+            Bounce& b = *c.bounce;
+            const int par = last == b.s_up[0] ? 0 : 1;
+            CU(cudaStreamWaitEvent(last, b.ev_up[par ^ 1], 0));
+        }
+        return SNAPPY_B200_OK;
+    }
+    int mark() {  // what the caller queued behind after() is now the latest thing on that stream
+        if (pageable && piece > 0) {
+            Bounce& b = *c.bounce;
+            const int par = last == b.s_up[0] ? 0 : 1;
+            CU(cudaEventRecord(b.ev_up[par], last));
+        }
+        return SNAPPY_B200_OK;
+    }
+    int sync() {
+        if (pageable)
+            for (int i = 0; i < 2; i++) CU(cudaStreamSynchronize(c.bounce->s_up[i]));
+        return SNAPPY_B200_OK;
+    }
+};
+
+// Device -> host for data that is ready on the device (the caller waited for it).
+struct Downloader {
+    Context& c;
+    bool pageable;
+    struct Piece {
+        u8* h_dst;
+        size_t len;
+        int slot;
+    };
+    Piece q[kBounceDown];
+    int head = 0, count = 0, next_slot = 0;
+    Downloader(Context& ctx, bool pg) : c(ctx), pageable(pg) {}
+    int drain_one() {
+        Bounce& b = *c.bounce;
+        const Piece p = q[head];
+        head = (head + 1) % kBounceDown;
+        count--;
+        CU(cudaEventSynchronize(b.ev_down[p.slot]));
+        CopyPool::get().copy(p.h_dst, b.pin + (size_t)(kBounceUp + p.slot) * kBounceSlot, p.len);
+        return SNAPPY_B200_OK;
+    }
+    int push(u8* h_dst, const u8* d_src, size_t len) {
+        if (!pageable) {
+            if (len) CU(cudaMemcpyAsync(h_dst, d_src, len, cudaMemcpyDeviceToHost, c.s_d2h));
+            return SNAPPY_B200_OK;
+        }
+        Bounce& b = *c.bounce;
+        for (size_t o = 0; o < len; o += kBounceSlot) {
+            const size_t l = len - o < kBounceSlot ? len - o : kBounceSlot;
+            if (count == kBounceDown) {
+                int rc = drain_one();
+                if (rc != SNAPPY_B200_OK) return rc;
+            }
+            const int slot = next_slot;
+            next_slot = (next_slot + 1) % kBounceDown;
+            CU(cudaMemcpyAsync(b.pin + (size_t)(kBounceUp + slot) * kBounceSlot, d_src + o, l, cudaMemcpyDeviceToHost, c.s_d2h));
+            CU(cudaEventRecord(b.ev_down[slot], c.s_d2h));
+            q[(head + count) % kBounceDown] = Piece{h_dst + o, l, slot};
+            count++;
+        }
+        return SNAPPY_B200_OK;
+    }
+    int finish() {
+        while (pageable && count) {
+            int rc = drain_one();
+            if (rc != SNAPPY_B200_OK) return rc;
+        }
+        return SNAPPY_B200_OK;
+    }
+};
+
+}  // namespace
+}  // extern "C++"
+
 // The streamed host paths enqueue copies from / into the CALLER's buffers on several streams.  Whatever way such a
 // function returns, nothing may still be in flight: an early error return drains the pipeline first.
 struct PipeGuard {
@@ -1233,6 +1517,9 @@ struct PipeGuard {
         if (drained) return;
         for (cudaStream_t st : {c.s_h2d, c.s_comp, c.side, c.s_pack, c.s_d2h})
             if (st) cudaStreamSynchronize(st);
+        if (c.bounce)
+            for (cudaStream_t st : c.bounce->s_up)
+                if (st) cudaStreamSynchronize(st);
     }
 };
 
@@ -1271,6 +1558,14 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
     const int k = encode_varint((u32)n, hdr);   // src/Snappy.jl:26
     u64* h_k = (u64*)((u8*)c.pinned + 96);
     *h_k = (u64)k;
+    // plain (pageable) caller buffers go through the pinned bounce slots, pinned ones straight
+    const bool pg_in = c.opt.pin_host && is_pageable(in), pg_out = c.opt.pin_host && is_pageable(out);
+    if (pg_in || pg_out) {
+        int rb = bounce_init(c);
+        if (rb != SNAPPY_B200_OK) return rb;
+    }
+    Uploader up(c, pg_in, n, nchunks);
+    Downloader down(c, pg_out);
     CU(cudaMemsetAsync(c.flags.p, 0, 64 + (size_t)nchunks * 4, c.s_comp));
     CU(cudaMemcpyAsync(d_out, hdr, (size_t)k, cudaMemcpyHostToDevice, c.s_comp));
     CU(cudaMemcpyAsync(running, h_k, 8, cudaMemcpyHostToDevice, c.s_comp));
@@ -1286,13 +1581,24 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
         const size_t tail_len = n - tail_start;
         CU(cudaMemcpyAsync(c.tail.p, in + tail_start, tail_len, cudaMemcpyHostToDevice, c.s_h2d));
         CU(cudaMemcpyAsync((u8*)c.tail.p + tail_len, c.pinned_zero, kTailPad, cudaMemcpyHostToDevice, c.s_h2d));
+        CU(cudaEventRecord(c.ev_in[1], c.s_h2d));
+    }
+    {
+        int ru = up.begin(c.ev_in[1]);  // behind the tail copy (which is behind the setup on s_comp)
+        if (ru != SNAPPY_B200_OK) return ru;
     }
     for (int i = 0; i < nchunks; i++) {
         const size_t off = (size_t)i * cf * kBlockSize;
         const size_t len = (n - off < cf * kBlockSize) ? (n - off) : cf * kBlockSize;
-        CU(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c.s_h2d));
+        int ru = up.put(d_in + off, in + off, len);
+        if (ru != SNAPPY_B200_OK) return ru;
         h_ready[i] = (i == nchunks - 1) ? nfrag : (u32)((size_t)(i + 1) * cf);
-        CU(cudaMemcpyAsync(d_ready, h_ready + i, 4, cudaMemcpyHostToDevice, c.s_h2d));
+        cudaStream_t us = nullptr;
+        ru = up.after(&us);  // the count follows every byte put so far, and the counts follow each other
+        if (ru != SNAPPY_B200_OK) return ru;
+        CU(cudaMemcpyAsync(d_ready, h_ready + i, 4, cudaMemcpyHostToDevice, us));
+        ru = up.mark();
+        if (ru != SNAPPY_B200_OK) return ru;
     }
     // the persistent kernels
     int launches = 0;
@@ -1322,12 +1628,21 @@ int compress_host_streamed(Context& c, const u8* in, size_t n, u8* out, size_t* 
     for (int i = 0; i < nchunks; i++) {
         CU(cudaEventSynchronize(c.ev_done[i]));
         const u64 end = ((volatile u64*)h_tot)[i];
-        CU(cudaMemcpyAsync(out + prev, d_out + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, c.s_d2h));
+        int rd = down.push(out + prev, d_out + prev, (size_t)(end - prev));
+        if (rd != SNAPPY_B200_OK) return rd;
         prev = end;
+    }
+    {
+        int rd = down.finish();
+        if (rd != SNAPPY_B200_OK) return rd;
     }
     CU(cudaStreamSynchronize(c.s_d2h));
     CU(cudaStreamSynchronize(c.s_comp));
     CU(cudaStreamSynchronize(c.s_h2d));
+    {
+        int ru = up.sync();
+        if (ru != SNAPPY_B200_OK) return ru;
+    }
     harvest_timing(c, 0);
     c.last_launches[0] = launches;
     *out_len = (size_t)prev;
@@ -1447,10 +1762,37 @@ int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32
     size_t cb[kChunks + 1];
     const size_t csz = ((n + kChunks - 1) / kChunks + 4095) & ~(size_t)4095;
     for (int i = 0; i <= kChunks; i++) cb[i] = ((size_t)i * csz < n) ? (size_t)i * csz : n;
+    const bool pg_in = c.opt.pin_host && is_pageable(in), pg_out = c.opt.pin_host && is_pageable(out);
+    if (pg_in || pg_out) {
+        int rb = bounce_init(c);
+        if (rb != SNAPPY_B200_OK) return rb;
+    }
+    Uploader up(c, pg_in, n, kChunks);
+    Downloader down(c, pg_out);
+    std::vector<Context::DownRange> ranges;
+    struct DeferGuard {
+        Context& c;
+        ~DeferGuard() { c.defer_down = nullptr; }
+    } defer_guard{c};
+    if (pg_out) c.defer_down = &ranges;
+    size_t drained = 0;
+    auto drain_ranges = [&](size_t upto) -> int {  // finished output ranges -> the caller's pageable buffer
+        for (; drained < upto && drained < ranges.size(); drained++) {
+            CU(cudaEventSynchronize(c.ev_done[ranges[drained].ev]));
+            int rd = down.push(out + ranges[drained].off, d_out + ranges[drained].off, ranges[drained].len);
+            if (rd != SNAPPY_B200_OK) return rd;
+        }
+        return SNAPPY_B200_OK;
+    };
     for (int i = 0; i < kChunks; i++) {
-        if (cb[i + 1] > cb[i])
-            CU(cudaMemcpyAsync(d_in + cb[i], in + cb[i], cb[i + 1] - cb[i], cudaMemcpyHostToDevice, c.s_h2d));
-        CU(cudaEventRecord(c.ev_in[i], c.s_h2d));
+        if (cb[i + 1] > cb[i]) {
+            int ru = up.put(d_in + cb[i], in + cb[i], cb[i + 1] - cb[i]);
+            if (ru != SNAPPY_B200_OK) return ru;
+        }
+        cudaStream_t us = nullptr;
+        int ru = up.after(&us);
+        if (ru != SNAPPY_B200_OK) return ru;
+        CU(cudaEventRecord(c.ev_in[i], us));
     }
     const bool dbg = getenv("SNAPPY_B200_DEBUG") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
@@ -1494,10 +1836,19 @@ int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32
                                    &ri, f_hi - f_done);
             if (r2 != SNAPPY_B200_OK) return r2;
             f_done = f_hi;
+            if (pg_out && ranges.size() > 1) {  // the range before this one has had a segment's time to finish
+                r2 = drain_ranges(ranges.size() - 1);
+                if (r2 != SNAPPY_B200_OK) return r2;
+            }
         }
     }
     if (rc > 0) return rc;
     if (rc == 0 && out_base != claimed) rc = -1;
+    if (pg_out && rc == 0) {
+        int r2 = drain_ranges(ranges.size());
+        if (r2 == SNAPPY_B200_OK) r2 = down.finish();
+        if (r2 != SNAPPY_B200_OK) return r2;
+    }
     if (dbg) {
         CU(cudaStreamSynchronize(st));
         CU(cudaStreamSynchronize(c.s_pack));
@@ -1506,6 +1857,10 @@ int uncompress_host_streamed(Context& c, const u8* in, size_t n, size_t hdr, u32
     const int rf = decode_finish(c, st, true);
     if (dbg) fprintf(stderr, "[snappy_b200] t=%.2f ms: copies done\n", ms());
     CU(cudaStreamSynchronize(c.s_h2d));
+    {
+        int ru = up.sync();
+        if (ru != SNAPPY_B200_OK) return ru;
+    }
     if (rf > 0) return rf;
     return (rc == 0 && rf == 0) ? SNAPPY_B200_OK : -1;
 }

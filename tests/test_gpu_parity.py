@@ -544,3 +544,33 @@ def test_streamed_uncompress_incompressible(snappy, oracle):
     assert want.size > raw.size
     assert np.array_equal(snappy.uncompress_np(want), raw)
     assert np.array_equal(snappy.compress_np(raw), want)
+
+
+def test_host_api_pinned_and_pageable_buffers_agree(snappy, oracle):
+    """the host-buffer C ABI takes pinned buffers straight and bounces pageable ones (a plain Vector{UInt8},
+    src/Snappy.jl:25,48) through pinned slots: same bytes either way, both directions, at a streamed size"""
+    import ctypes
+    import torch
+    from snappy_jl_b200 import synth
+    raw = synth.mix(2100, seed=77, tail=333)
+    want = oracle.compress_np(raw)
+    lib = snappy._abi.lib()
+    cap = snappy.maxlength_compressed(raw.size)
+    pin_in = torch.from_numpy(raw.copy()).pin_memory()
+    pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    pin_back = torch.empty(raw.size, dtype=torch.uint8).pin_memory()
+    pg_in = raw.copy()
+    pg_out = np.empty(cap, dtype=np.uint8)
+    pg_back = np.empty(raw.size, dtype=np.uint8)
+    for name, (i, o, b) in {"pinned": (pin_in.data_ptr(), pin_out.data_ptr(), pin_back.data_ptr()),
+                            "pageable": (pg_in.ctypes.data, pg_out.ctypes.data, pg_back.ctypes.data),
+                            "pinned in, pageable out": (pin_in.data_ptr(), pg_out.ctypes.data, pg_back.ctypes.data)}.items():
+        ol = ctypes.c_size_t(cap)
+        assert lib.snappy_b200_compress(i, raw.size, o, ctypes.byref(ol)) == 0, name
+        got = (pin_out.numpy() if o == pin_out.data_ptr() else pg_out)[: ol.value]
+        assert ol.value == want.size and np.array_equal(got, want), name
+        bl = ctypes.c_size_t(raw.size)
+        assert lib.snappy_b200_uncompress(o, ol.value, b, ctypes.byref(bl)) == 0, name
+        back = pin_back.numpy() if b == pin_back.data_ptr() else pg_back
+        assert bl.value == raw.size and np.array_equal(back, raw), name
+        back[:] = 0

@@ -242,6 +242,12 @@ static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
     if (v > old) *p = v;
     return old;
 }
+template <typename T>
+static inline T atomicMin(T* p, T v) {
+    const T old = *p;
+    if (v < old) *p = v;
+    return old;
+}
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
     const uint32_t old = *p;
     *p = old | v;

@@ -109,8 +109,8 @@ static SegResult parse_segment(const u8* in, u64 n, u64 hdr, u64 E, u64 out_base
     std::vector<u64> out_off(nchunk + 1, 0);  // k_scan_sizes: exclusive scan, total behind the end
     for (u32 k = 0; k < nchunk; k++) out_off[k + 1] = out_off[k] + pa.outb[k];
     launch_independent_threads(pgrid, kParseThreads, k_build_index, in, n, hdr, nchunk, pa, (const u64*)out_off.data(), index, nfrag,
-                               E, out_base, pshift);
-    u64 host3[3];
+                               E, out_base, pshift, (u64*)nullptr, 0u, (u64)0);  // strict form: aligned tiles only
+    u64 host3[4];
     k_parse_report(pa.counters, out_off.data() + nchunk, host3);
     return SegResult{host3[0], host3[1], host3[2]};
 }
