@@ -37,17 +37,15 @@
 namespace sb200 {
 
 constexpr u32 kRingChunk = 512;  // bytes staged per step (one 16-byte load per lane)
-// SB200_PREFETCH (experiment): 1 = shared-table warps, 2 = all warps look the NEXT window's positions up in the table
-// as well and prefetch their far candidates into L2 (a hint: the lookups are repeated next round)
-#ifndef SB200_PREFETCH
-#define SB200_PREFETCH 0
-#endif
-constexpr u32 kRingAhead = SB200_PREFETCH ? 96 : 64;   // bytes past the window start that must be resident
+constexpr u32 kRingAhead = 64;   // bytes past the window start that must be resident (+ 32 for the two-window round)
 constexpr u32 kRingMirror = 32;  // the first bytes of the ring are repeated behind its end: a 20-byte read never wraps
 #ifndef SB200_FAR_ALL
 #define SB200_FAR_ALL 1
 #endif
 constexpr bool kFarAll = SB200_FAR_ALL != 0;
+#ifdef SB200_CPU_EMU
+static unsigned long g_emu_rounds = 0, g_emu_second = 0;  // tools/cpu_warp: rounds run / second windows entered
+#endif
 #ifndef SB200_M_BRANCHFREE
 #define SB200_M_BRANCHFREE 1
 #endif
@@ -56,7 +54,13 @@ constexpr bool kFarAll = SB200_FAR_ALL != 0;
 // chain goes on in the same window when it lands there, instead of ending the round (tools/emulate_window.c
 // SLOWCONT=1: 1-8 % fewer rounds).  Exact (tools/cpu_warp, and byte-identical on the B200); measured 13.58 vs 13.12 ms
 // per GiB: slower, so off.
-template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
+// kTwo (the two-window round): every round evaluates 64 positions, two per lane.  The first window is resolved as
+// always; when the chain leaves it into the second one (a scan that runs off its end, a copy that lands up to 15
+// bytes behind it) the second window is NOT evaluated again: its lanes re-read their table entry, a lane whose entry
+// changed since the round start is untrusted (entries only grow, so any insert with its hash shows), and the chain is
+// followed on.  The evaluation -- ring loads, hash, table lookup, candidate gather from L2 / DRAM, match length -- is
+// the latency-bound part of a round, and the two windows' loads overlap.  (tools/emulate_window.c WW=2 is the model.)
+template <bool kSmemTable, bool kLib = false, bool kSlowCont = false, bool kTwo = false>
 struct Win : Chain<kSmemTable, kLib> {
     using Base = Chain<kSmemTable, kLib>;
     using Base::F;
@@ -97,14 +101,6 @@ struct Win : Chain<kSmemTable, kLib> {
     __device__ __forceinline__ uint4 load_chunk(u32 p) const {
         uint4 v;
         if (aligned16) {
-#if defined(SB200_STAGE_EL) && !defined(SB200_CPU_EMU)
-            // experiment: the staged chunk's lines get the L2 evict_last priority (1: every warp, 2: shared-table warps)
-            if (SB200_STAGE_EL == 1 || kSmemTable)
-                asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; "
-                             "ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol; }"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(F + p) : "memory");
-            else
-#endif
             v = __ldg(reinterpret_cast<const uint4*>(F + p));
         } else {
             v.x = ldg32u(F + p);
@@ -180,6 +176,95 @@ struct Win : Chain<kSmemTable, kLib> {
         return M;
     }
 
+    // One window: lane's position q as if the chain arrived there -- hash of its 4 bytes (:94), table lookup against
+    // the table AS IT IS NOW, common prefix of candidate and position over 16 bytes (find_match_length, capped).
+    //   H hash, t candidate position, m equal bytes (0 for an invalid lane), mp lanes with the same hash
+    __device__ __forceinline__ void evaluate(const u32 q, const bool V, u32& H, u32& t, u32& m, u32& mp) const {
+        u32 B0, B1, B2, B3;
+        {
+            const u32 qb = q & ~3u, sh = q << 3;
+            const u32 ab = Rs + (qb & rmask);
+            const u32 w0 = lds32o<0>(ab), w1 = lds32o<4>(ab), w2 = lds32o<8>(ab), w3 = lds32o<12>(ab),
+                      w4 = lds32o<16>(ab);
+            B0 = __funnelshift_r(w0, w1, sh);
+            B1 = __funnelshift_r(w1, w2, sh);
+            B2 = __funnelshift_r(w2, w3, sh);
+            B3 = __funnelshift_r(w3, w4, sh);
+        }
+        H = this->hash(B0);
+        t = V ? this->tget(H) : lo;
+        mp = __match_any_sync(kFullMask, V ? H : (0x80000000u | lane));
+        // candidate bytes, straight-line: recent candidates come from the ring (5 words), old
+        // ones from L1/L2 (2 words = the 4 bytes that decide a hit; the other 3 only on a hit)
+        const u32 nearp = (t >= lo) ? 1u : 0u;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(F + t);  // F need not be 4-byte aligned
+        const u32* g = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
+        const u32 tb = t & ~3u, tsh = (nearp ? t : (u32)ga) << 3;
+        u32 c0, c1, c2 = 0, c3 = 0, c4 = 0;
+        // far_all: old candidates fetch all 16 bytes at once (one L2 round trip, more wavefronts)
+        // instead of 4 bytes first and the other 12 on a hit
+        const u32 far_all = kFarAll ? 1u : 0u;
+#ifdef SB200_CPU_EMU
+        if (nearp) {
+            const u32 ra = Rs + (tb & rmask);
+            c0 = lds32o<0>(ra); c1 = lds32o<4>(ra); c2 = lds32o<8>(ra); c3 = lds32o<12>(ra); c4 = lds32o<16>(ra);
+        } else {
+            c0 = g[0]; c1 = g[1];
+            if (far_all) { c2 = g[2]; c3 = g[3]; c4 = g[4]; }
+        }
+#else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.u32 p, %5, 0;\n"
+            "@p ld.shared.u32 %0, [%6];\n"
+            "@p ld.shared.u32 %1, [%6+4];\n"
+            "@p ld.shared.u32 %2, [%6+8];\n"
+            "@p ld.shared.u32 %3, [%6+12];\n"
+            "@p ld.shared.u32 %4, [%6+16];\n"
+            "@!p ld.global.nc.u32 %0, [%7];\n"
+            "@!p ld.global.nc.u32 %1, [%7+4];\n"
+            "setp.ne.and.u32 p, %8, 0, !p;\n"
+            "@p ld.global.nc.u32 %2, [%7+8];\n"
+            "@p ld.global.nc.u32 %3, [%7+12];\n"
+            "@p ld.global.nc.u32 %4, [%7+16];\n"
+            "}\n"
+            : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+            : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
+            : "memory");
+#endif
+        u32 C0 = __funnelshift_r(c0, c1, tsh);
+        const bool more = V && !nearp && !far_all && C0 == B0;
+        if (__any_sync(kFullMask, more)) {
+            if (more) {
+                c2 = __ldg(g + 2);
+                c3 = __ldg(g + 3);
+                c4 = __ldg(g + 4);
+            }
+        }
+        m = 0;
+        {
+            const u32 x0 = C0 ^ B0, x1 = __funnelshift_r(c1, c2, tsh) ^ B1,
+                      x2 = __funnelshift_r(c2, c3, tsh) ^ B2, x3 = __funnelshift_r(c3, c4, tsh) ^ B3;
+#if SB200_M_BRANCHFREE
+            // equal bytes per word (0..4), then the length of the run of full words: no divergent branches
+            const u32 m0 = x0 ? ((u32)__ffs((int)x0) - 1u) >> 3 : 4u, m1 = x1 ? ((u32)__ffs((int)x1) - 1u) >> 3 : 4u,
+                      m2 = x2 ? ((u32)__ffs((int)x2) - 1u) >> 3 : 4u, m3 = x3 ? ((u32)__ffs((int)x3) - 1u) >> 3 : 4u;
+            const bool f0 = m0 == 4u, f1 = f0 && m1 == 4u, f2 = f1 && m2 == 4u;
+            m = m0 + (f0 ? m1 : 0u) + (f1 ? m2 : 0u) + (f2 ? m3 : 0u);
+#else
+            if (x0) m = ((u32)__ffs((int)x0) - 1u) >> 3;
+            else if (x1) m = 4u + (((u32)__ffs((int)x1) - 1u) >> 3);
+            else if (x2) m = 8u + (((u32)__ffs((int)x2) - 1u) >> 3);
+            else if (x3) m = 12u + (((u32)__ffs((int)x3) - 1u) >> 3);
+            else m = 16u;
+#endif
+            if (!V) m = 0;
+        }
+    }
+
+    enum : u32 { K_COPY = 0, K_SLOW = 1, K_FIN = 2, K_NEXTSCAN = 3, K_NEXTARR = 4, K_LEAVE = 5 };
+
     __device__ __forceinline__ void run_window() {
         asm volatile("" : "+r"(this->n), "+r"(this->Ts), "+r"(this->shift), "+r"(Rs), "+r"(rmask));
         this->op = 0;
@@ -208,131 +293,36 @@ struct Win : Chain<kSmemTable, kLib> {
                     continue;
                 }
                 // ------------- lane evaluation against the table as of the round start
-                if (a + kRingAhead > hi) stage_to(a + kRingAhead);
+                if (a + kRingAhead + (kTwo ? 32u : 0u) > hi) stage_to(a + kRingAhead + (kTwo ? 32u : 0u));
                 if (arrival) {  // :233 the position before an arrival is inserted first
                     if (lane == 0) this->tput(this->hash(ring32u(a - 1u)), a - 1u);
                     __syncwarp();
                 }
-                const u32 q = a + lane;
-                const bool V = (int)q < lim;
-                u32 B0, B1, B2, B3;
-                {
-                    const u32 qb = q & ~3u, sh = q << 3;
-                    const u32 ab = Rs + (qb & rmask);
-                    const u32 w0 = lds32o<0>(ab), w1 = lds32o<4>(ab), w2 = lds32o<8>(ab), w3 = lds32o<12>(ab),
-                              w4 = lds32o<16>(ab);
-                    B0 = __funnelshift_r(w0, w1, sh);
-                    B1 = __funnelshift_r(w1, w2, sh);
-                    B2 = __funnelshift_r(w2, w3, sh);
-                    B3 = __funnelshift_r(w3, w4, sh);
-                }
-                const u32 H = this->hash(B0);
-                const u32 t = V ? this->tget(H) : lo;
-#if SB200_PREFETCH && !defined(SB200_CPU_EMU)
-                u32 t_next = 0xffffffffu;  // candidate of position q + 32 by the table as it is now
-                if ((kSmemTable || SB200_PREFETCH >= 2) && (int)(q + 32u) < lim) t_next = this->tget(this->hash(ring32u(q + 32u)));
-#endif
-                const u32 mp = __match_any_sync(kFullMask, V ? H : (0x80000000u | lane));
-                // candidate bytes, straight-line: recent candidates come from the ring (5 words), old
-                // ones from L1/L2 (2 words = the 4 bytes that decide a hit; the other 3 only on a hit)
-                const u32 nearp = (t >= lo) ? 1u : 0u;
-                const uintptr_t ga = reinterpret_cast<uintptr_t>(F + t);  // F need not be 4-byte aligned
-                const u32* g = reinterpret_cast<const u32*>(ga & ~(uintptr_t)3);
-                const u32 tb = t & ~3u, tsh = (nearp ? t : (u32)ga) << 3;
-                u32 c0, c1, c2 = 0, c3 = 0, c4 = 0;
-                // far_all: old candidates fetch all 16 bytes at once (one L2 round trip, more wavefronts)
-                // instead of 4 bytes first and the other 12 on a hit
-                const u32 far_all = kFarAll ? 1u : 0u;
 #ifdef SB200_CPU_EMU
-                if (nearp) {
-                    const u32 ra = Rs + (tb & rmask);
-                    c0 = lds32o<0>(ra); c1 = lds32o<4>(ra); c2 = lds32o<8>(ra); c3 = lds32o<12>(ra); c4 = lds32o<16>(ra);
-                } else {
-                    c0 = g[0]; c1 = g[1];
-                    if (far_all) { c2 = g[2]; c3 = g[3]; c4 = g[4]; }
-                }
-#else
-#if defined(SB200_FAR_EF)
-                // experiment: far candidates of the global-table warps leave L2 first (evict_first), so that they do
-                // not push out the lines the shared-table warps gather from
-                if (!kSmemTable) {
-                    asm volatile(
-                        "{\n"
-                        ".reg .pred p;\n"
-                        ".reg .b64 pol;\n"
-                        "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
-                        "setp.ne.u32 p, %5, 0;\n"
-                        "@p ld.shared.u32 %0, [%6];\n"
-                        "@p ld.shared.u32 %1, [%6+4];\n"
-                        "@p ld.shared.u32 %2, [%6+8];\n"
-                        "@p ld.shared.u32 %3, [%6+12];\n"
-                        "@p ld.shared.u32 %4, [%6+16];\n"
-                        "@!p ld.global.nc.L2::cache_hint.u32 %0, [%7], pol;\n"
-                        "@!p ld.global.nc.L2::cache_hint.u32 %1, [%7+4], pol;\n"
-                        "@!p ld.global.nc.L2::cache_hint.u32 %2, [%7+8], pol;\n"
-                        "@!p ld.global.nc.L2::cache_hint.u32 %3, [%7+12], pol;\n"
-                        "@!p ld.global.nc.L2::cache_hint.u32 %4, [%7+16], pol;\n"
-                        "}\n"
-                        : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
-                        : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
-                        : "memory");
-                } else
+                if (lane == 0) g_emu_rounds++;
 #endif
-                asm volatile(
-                    "{\n"
-                    ".reg .pred p;\n"
-                    "setp.ne.u32 p, %5, 0;\n"
-                    "@p ld.shared.u32 %0, [%6];\n"
-                    "@p ld.shared.u32 %1, [%6+4];\n"
-                    "@p ld.shared.u32 %2, [%6+8];\n"
-                    "@p ld.shared.u32 %3, [%6+12];\n"
-                    "@p ld.shared.u32 %4, [%6+16];\n"
-                    "@!p ld.global.nc.u32 %0, [%7];\n"
-                    "@!p ld.global.nc.u32 %1, [%7+4];\n"
-                    "setp.ne.and.u32 p, %8, 0, !p;\n"
-                    "@p ld.global.nc.u32 %2, [%7+8];\n"
-                    "@p ld.global.nc.u32 %3, [%7+12];\n"
-                    "@p ld.global.nc.u32 %4, [%7+16];\n"
-                    "}\n"
-                    : "=r"(c0), "=r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
-                    : "r"(nearp), "r"(Rs + (tb & rmask)), "l"(g), "r"(far_all)
-                    : "memory");
-#endif
-                u32 C0 = __funnelshift_r(c0, c1, tsh);
-                const bool more = V && !nearp && !far_all && C0 == B0;
-                if (__any_sync(kFullMask, more)) {
-                    if (more) {
-                        c2 = __ldg(g + 2);
-                        c3 = __ldg(g + 3);
-                        c4 = __ldg(g + 4);
-                    }
+                u32 q = a + lane;
+                bool V = (int)q < lim;
+                u32 H, t, m, mp;
+                evaluate(q, V, H, t, m, mp);
+                // the second window of the round (kTwo): evaluated now, used only if the chain gets there
+                u32 H1 = 0, t1 = 0, m1 = 0, mp1 = 0;
+                bool V1 = false;
+                const bool have_hi = kTwo && (int)(a + 32u) < lim;
+                if (have_hi) {
+                    V1 = (int)(q + 32u) < lim;
+                    evaluate(q + 32u, V1, H1, t1, m1, mp1);
                 }
-                u32 m = 0;
-                {
-                    const u32 x0 = C0 ^ B0, x1 = __funnelshift_r(c1, c2, tsh) ^ B1,
-                              x2 = __funnelshift_r(c2, c3, tsh) ^ B2, x3 = __funnelshift_r(c3, c4, tsh) ^ B3;
-#if SB200_M_BRANCHFREE
-                    // equal bytes per word (0..4), then the length of the run of full words: no divergent branches
-                    const u32 m0 = x0 ? ((u32)__ffs((int)x0) - 1u) >> 3 : 4u, m1 = x1 ? ((u32)__ffs((int)x1) - 1u) >> 3 : 4u,
-                              m2 = x2 ? ((u32)__ffs((int)x2) - 1u) >> 3 : 4u, m3 = x3 ? ((u32)__ffs((int)x3) - 1u) >> 3 : 4u;
-                    const bool f0 = m0 == 4u, f1 = f0 && m1 == 4u, f2 = f1 && m2 == 4u;
-                    m = m0 + (f0 ? m1 : 0u) + (f1 ? m2 : 0u) + (f2 ? m3 : 0u);
-#else
-                    if (x0) m = ((u32)__ffs((int)x0) - 1u) >> 3;
-                    else if (x1) m = 4u + (((u32)__ffs((int)x1) - 1u) >> 3);
-                    else if (x2) m = 8u + (((u32)__ffs((int)x2) - 1u) >> 3);
-                    else if (x3) m = 12u + (((u32)__ffs((int)x3) - 1u) >> 3);
-                    else m = 16u;
-#endif
-                    if (!V) m = 0;
-                }
+                u32 changed = 0, entry = 0;  // second window: lanes whose table entry moved; lane the chain enters at
+                u32 d, insacc, cur;
+                for (u32 half = 0;; half++) {
                 const u32 vmask = __ballot_sync(kFullMask, V);
                 const u32 hitmask = __ballot_sync(kFullMask, m >= 4u);
-                const u32 dupmask = __ballot_sync(kFullMask, (mp & ((1u << lane) - 1u)) != 0u);
+                // untrusted lanes: hash equal to a lower lane's; in the second window also a table entry that moved
+                const u32 dupmask = __ballot_sync(kFullMask, (mp & ((1u << lane) - 1u)) != 0u) | changed;
                 const u32 tm = (t << 16) | (m << 8);
                 // ------------- per-lane descriptor: what happens when the chain ARRIVES at this lane
                 //   bits 0-2 kind, 3-7 lane e of the event, 8-12 copy length, 16-31 candidate, bit 13 = a scan started
-                enum : u32 { K_COPY = 0, K_SLOW = 1, K_FIN = 2, K_NEXTSCAN = 3, K_NEXTARR = 4, K_LEAVE = 5 };
                 const u32 stop_all = ~vmask | dupmask | hitmask;
                 u32 desc, ins;
                 {
@@ -343,7 +333,9 @@ struct Win : Chain<kSmemTable, kLib> {
                     // (selects, no branches: the lanes differ in all of these)
                     const bool hit = (hitmask & lbit) != 0u, none = rest == 0u;
                     const bool ev_invalid = (vmask & ebit) == 0u, ev_dup = (dupmask & ebit) != 0u;  // :175
-                    const bool untrusted = lane != 0u && (dupmask & lbit) != 0u;  // the next round starts here
+                    // the next round starts at an untrusted lane (lane 0 of a round's first window looked the
+                    // committed table up and is never one)
+                    const bool untrusted = (lane != 0u || half != 0u) && (dupmask & lbit) != 0u;
                     const u32 above = (lane < 31u) ? (~0u << (lane + 1u)) : 0u;
                     const u32 kind_scan = none ? (u32)K_LEAVE
                                                : (ev_invalid ? (u32)K_FIN : (ev_dup ? (u32)K_NEXTSCAN : (u32)K_COPY));
@@ -361,10 +353,10 @@ struct Win : Chain<kSmemTable, kLib> {
                 }
                 // a round that starts inside a scan: the same from "lane -1", and the scan also stops
                 // where its probe count reaches 32 (:162-172)
-                u32 d, insacc, cur = 0;
+                cur = entry;
                 if (arrival) {
-                    d = __shfl_sync(kFullMask, desc, 0);
-                    insacc = __shfl_sync(kFullMask, ins, 0);
+                    d = __shfl_sync(kFullMask, desc, entry);
+                    insacc = __shfl_sync(kFullMask, ins, entry);
                 } else {
                     const u32 klim = 32u - (a - scan_s);  // 1..32
                     const u32 limmask = klim < 32u ? ~((1u << klim) - 1u) : 0u;
@@ -425,14 +417,41 @@ struct Win : Chain<kSmemTable, kLib> {
                     d = __shfl_sync(kFullMask, desc, cur);
                     insacc |= __shfl_sync(kFullMask, ins, cur);
                 }
-                const u32 kind = d & 7u, ev = (d >> 3) & 31u;
                 const u32 ins_all = insacc;
-#if SB200_PREFETCH && !defined(SB200_CPU_EMU)
-                if (t_next < lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(F + t_next));
-#endif
                 // ------------- commit the inserts of the path; the highest position wins (:191)
                 if (((ins_all >> lane) & 1u) && (mp & ins_all & ~((2u << lane) - 1u)) == 0u) this->tput(H, q);
                 __syncwarp();
+                if (kTwo && half == 0u && have_hi) {
+                    // does the chain go on in the second window?  a scan that ran off the first one (and has probes
+                    // left at stride 1, :162-172), or a copy that landed behind it
+                    const u32 k0 = d & 7u;
+                    const bool leave = k0 == K_LEAVE && a + 32u - scan_s < 32u;
+                    const bool landed = k0 == K_NEXTARR && (d & (1u << 14)) && lit_from - (a + 32u) < 32u;
+                    if (leave || landed) {
+#ifdef SB200_CPU_EMU
+                        if (lane == 0) g_emu_second++;
+#endif
+                        entry = landed ? lit_from - (a + 32u) : 0u;
+                        arrival = landed;
+                        if (landed && entry == 0u && lane == 31u) this->tput(H, q);  // :233 position a + 31 goes in first
+                        a += 32u;
+                        __syncwarp();
+                        // the second window's lookups are as old as the round: any insert since then with a lane's
+                        // hash has replaced its entry (positions only grow)
+                        const u32 tnow = V1 ? this->tget(H1) : t1;
+                        changed = __ballot_sync(kFullMask, V1 && tnow != t1);
+                        q += 32u;
+                        V = V1;
+                        H = H1;
+                        t = t1;
+                        m = m1;
+                        mp = mp1;
+                        continue;
+                    }
+                }
+                break;
+                }  // sub-rounds
+                const u32 kind = d & 7u, ev = (d >> 3) & 31u;
                 if (kind == K_SLOW) {  // copy of >= 16 bytes: the whole warp extends it
                     const u32 ip = a + ev, cand = d >> 16;
                     const u32 M = extend(ip, cand, 16);
@@ -484,7 +503,7 @@ struct WindowArgs {
 // The life of one persistent warp: pull a fragment, clear the table, run the window rounds, record the size.
 //   T / ring : this warp's table (shared or global memory) and ring (shared-space address)
 //   kLib (option `rules`): libsnappy's rules, table sized per fragment; rules = 2: 64 KiB tables.
-template <bool kSmemTable, bool kLib, bool kSlowCont>
+template <bool kSmemTable, bool kLib, bool kSlowCont, bool kTwo = false>
 __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u32 ring, u32 ring_bytes, u32 tab,
                                                  u32 reserve) {
     const u32 lane = lane_id();
@@ -533,7 +552,7 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        Win<kSmemTable, kLib, kSlowCont> ch;
+        Win<kSmemTable, kLib, kSlowCont, kTwo> ch;
         ch.hmask = entries - 1u;
         ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;
@@ -592,8 +611,9 @@ k_compress_window(const WindowArgs A, u32 ring_bytes) {
 // warps next to it (a text fragment took 3.6 ms on a shared-table warp with the other kernel running, 2.0 ms alone;
 // profiles/r02b_trace_fragments.txt).  One kernel is also what lets ncu measure the pair as it really runs.
 // Shared memory: wa tables, then wa rings of ring_a bytes, then wb rings of ring_b bytes.
-template <bool kLib = false>
-__global__ void __launch_bounds__(704, 1)
+// kTwoA / kTwoB: the two-window round (Win<.., kTwo>) for the shared-table / global-table warps.
+template <bool kLib = false, bool kTwoA = false, bool kTwoB = false>
+__global__ void __launch_bounds__(640, 1)
 k_compress_window_mixed(const WindowArgs A, u32 wa, u32 wb, u32 ring_a, u32 ring_b, u32 smem_first) {
     extern __shared__ __align__(128) u8 smem[];
     const u32 warp = threadIdx.x >> 5;
@@ -604,12 +624,12 @@ k_compress_window_mixed(const WindowArgs A, u32 wa, u32 wb, u32 ring_a, u32 ring
     if (is_smem) {
         const u32 w = smem_first ? warp : warp - wb;
         u16* T = reinterpret_cast<u16*>(smem) + (size_t)w * tab;
-        window_warp_loop<true, kLib, false>(A, T, rings + w * (ring_a + kRingMirror), ring_a, tab, 0u);
+        window_warp_loop<true, kLib, false, kTwoA>(A, T, rings + w * (ring_a + kRingMirror), ring_a, tab, 0u);
     } else {
         const u32 w = smem_first ? warp - wa : warp;
         u16* T = A.gtables + ((size_t)blockIdx.x * wb + w) * tab;
-        window_warp_loop<false, kLib, false>(A, T, rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror),
-                                             ring_b, tab, A.reserve);
+        window_warp_loop<false, kLib, false, kTwoB>(A, T, rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror),
+                                                    ring_b, tab, A.reserve);
     }
 }
 

@@ -93,6 +93,7 @@ struct Options {
     int profile_range = 0;      // 1 = cudaProfilerStart/Stop around the concurrent compress kernels (ncu --replay-mode range)
     int mixed = 1;              // 1 = both table placements in ONE kernel, shared-table warps on the high warp numbers;
                                 // 2 = the same with them on the low ones; 0 = two concurrent kernels (round 1)
+    int two = 0;                // two-window round: 1 = global-table warps, 2 = shared-table warps, 3 = both (mixed kernel)
     int l2_first = 0;           // mixed = 0 only: launch the global-table kernel before the shared-table kernel
     int pages_window = 1;       // batched pages <= 8 KiB: window-round kernel (0 = the serial page kernel for every size)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
@@ -212,6 +213,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "pages_window")) g_opt.pages_window = value;
     else if (!strcmp(name, "mixed")) g_opt.mixed = value;
     else if (!strcmp(name, "l2_first")) g_opt.l2_first = value;
+    else if (!strcmp(name, "two")) g_opt.two = value;
     else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
     else if (!strcmp(name, "trace")) g_opt.trace = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
@@ -225,6 +227,9 @@ int set_kernel_attributes() {
                             (int)(kCompressSmemBytes + kMaxTableEntries * 2)));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_pages_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_pages_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // both window kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
@@ -568,15 +573,23 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
 #ifdef SB200_EXPERIMENTS
     plain = !(window && c.opt.slowcont) && window;
 #endif
-    if (plain && ctas_a && ctas_b && c.opt.mixed && c.opt.l2_ctas == 1 && wa + wb <= 22 && smem_a + smem_b <= 227 * 1024) {
+    if (plain && ctas_a && ctas_b && c.opt.mixed && c.opt.l2_ctas == 1 && wa + wb <= 20 && smem_a + smem_b <= 227 * 1024) {
         // the default: both table placements in one CTA per SM (the global-table rows of `gtables` are indexed by
         // CTA, so the grid is the shared-table grid: one CTA per SM)
+        const u32 sf = c.opt.mixed == 2 ? 1u : 0u;
+        const dim3 grid((unsigned)c.sm_count), block((wa + wb) * 32);
+        const size_t sm = smem_a + smem_b;
+        // option `two`: the two-window round for the global-table warps (1), the shared-table warps (2), both (3)
         if (rules)
-            k_compress_window_mixed<true><<<c.sm_count, (wa + wb) * 32, smem_a + smem_b, st>>>(
-                A, wa, wb, ra, rb, c.opt.mixed == 2 ? 1u : 0u);
+            k_compress_window_mixed<true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.two == 1)
+            k_compress_window_mixed<false, false, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.two == 2)
+            k_compress_window_mixed<false, true, false><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.two == 3)
+            k_compress_window_mixed<false, true, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         else
-            k_compress_window_mixed<false><<<c.sm_count, (wa + wb) * 32, smem_a + smem_b, st>>>(
-                A, wa, wb, ra, rb, c.opt.mixed == 2 ? 1u : 0u);
+            k_compress_window_mixed<false><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         *launches += 1;
         if (prof) {
             CU(cudaStreamSynchronize(st));
@@ -1267,8 +1280,10 @@ namespace {
 class CopyPool {  // a few persistent threads that split one memcpy among themselves (and the caller)
    public:
     static CopyPool& get() {
-        static CopyPool p;
-        return p;
+        // never destroyed: its threads sleep on the condition variable until the process ends (destroying a
+        // condition variable that has waiters blocks, which would hang the process at exit)
+        static CopyPool* p = new CopyPool();
+        return *p;
     }
     void copy(void* dst, const void* src, size_t n) {
         if (n < (4u << 20) || th_.empty()) {
@@ -1403,6 +1418,11 @@ struct Uploader {
     Uploader(Context& ctx, bool pg, size_t total_bytes, int extra) : c(ctx), pageable(pg) {
         if (pageable) jobs.reserve(total_bytes / kBounceSlot + (size_t)extra + 8);
         last = c.s_h2d;
+    }
+    ~Uploader() {  // the host functions read `jobs`: nothing of ours may be pending when it goes away
+        if (pageable && piece > 0 && c.bounce)
+            for (cudaStream_t s : c.bounce->s_up)
+                if (s) cudaStreamSynchronize(s);
     }
     int begin(cudaEvent_t after_this) {  // the upload streams start behind `after_this` (recorded by the caller)
         if (!pageable) return SNAPPY_B200_OK;
@@ -2300,7 +2320,7 @@ int snappy_b200_get_option(const char* name) {
         {"host_pipeline", o.host_pipeline}, {"timing", o.timing}, {"l2_persist", o.l2_persist},
         {"overlap_compact", o.overlap_compact}, {"window", o.window}, {"wide", o.wide}, {"slowcont", o.slowcont},
         {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host}, {"trace", o.trace},
-        {"profile_range", o.profile_range}, {"pages_window", o.pages_window}, {"mixed", o.mixed}, {"l2_first", o.l2_first},
+        {"profile_range", o.profile_range}, {"pages_window", o.pages_window}, {"mixed", o.mixed}, {"l2_first", o.l2_first}, {"two", o.two},
     };
     for (const auto& e : tab)
         if (!strcmp(name, e.n)) return e.v;

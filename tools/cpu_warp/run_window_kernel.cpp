@@ -30,6 +30,7 @@ struct Args {
     bool chain;  // KERNEL=chain: the step-wise kernel (option window=0), rules 0 only
     bool slowcont;  // SLOWCONT=1: the experimental window variant (option slowcont), rules 0 only
     bool mixed;     // MIXED=1: k_compress_window_mixed (one CTA holds both table placements)
+    bool two;       // TWO=1 (with MIXED=1, rules 0): the two-window round
 };
 
 static WindowArgs wargs(const Args& a) {
@@ -52,7 +53,8 @@ template <bool kSmem, bool kLib>
 static void launch(const Args& a) {
     if (a.mixed) {  // the default launch form: both placements in one CTA; this warp plays the role TABLE names
         // CTA of wb = 1 global-table warp and wa = 1 shared-table warp: warp 0 / warp 1 (the harness sets tid_base)
-        k_compress_window_mixed<kLib>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        if (a.two && !kLib) k_compress_window_mixed<false, true, true>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        else k_compress_window_mixed<kLib>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
         return;
     }
     k_compress_window<kSmem, kLib>(wargs(a), a.ring);
@@ -88,6 +90,7 @@ int main(int argc, char** argv) {
     const bool chain = getenv("KERNEL") && !strcmp(getenv("KERNEL"), "chain");
     const bool slowcont = getenv("SLOWCONT") && atoi(getenv("SLOWCONT")) != 0;
     const bool mixed = getenv("MIXED") && atoi(getenv("MIXED")) != 0;
+    const bool two = getenv("TWO") && atoi(getenv("TWO")) != 0;
     if ((chain || slowcont) && rules) {
         fprintf(stderr, "KERNEL=chain has no rules instantiation\n");
         return 2;
@@ -123,7 +126,7 @@ int main(int argc, char** argv) {
         u32 counter = 0;
         u32 entries = sjo_hashtable_entries((u64)sz), shift = 32;
         for (u32 e = entries; e > 1; e >>= 1) shift--;
-        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont, mixed};
+        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont, mixed, two};
         cpu_warp::W().collectives = 0;
         if (mixed) {  // CTA of two warps: warp 0 = global-table role, warp 1 = shared-table role
             cpu_warp::W().block = 0;
@@ -151,6 +154,8 @@ int main(int argc, char** argv) {
                 if (bad++ < 3) fprintf(stderr, "%s: fragment %u differs (%u vs %zu bytes)\n", argv[ai], f, sizes[f], c);
             }
         }
+        if (getenv("ROUNDS")) printf("rounds %lu, second windows entered %lu\n", sb200::g_emu_rounds, sb200::g_emu_second);
+        sb200::g_emu_rounds = sb200::g_emu_second = 0;
         printf("%s: %u fragments, %ld mismatches (%s kernel, %s table, rules %u, ring %u, %llu collectives)\n", argv[ai], nfrag, bad,
                chain ? "chain" : (slowcont ? "window+slowcont" : "window"), smem_table ? "shared" : "global", rules, ring, (unsigned long long)cpu_warp::W().collectives);
         failed += bad != 0;
