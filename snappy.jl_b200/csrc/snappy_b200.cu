@@ -178,6 +178,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "slowcont")) g_opt.slowcont = value != 0;
     else if (!strcmp(name, "window")) g_opt.window = value;
     else if (!strcmp(name, "wide")) g_opt.wide = value;
+    else if (!strcmp(name, "two")) g_opt.two = value;
 #endif
     else if (!strcmp(name, "smem_chains")) g_opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
     else if (!strcmp(name, "l2_chains")) g_opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
@@ -213,7 +214,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "pages_window")) g_opt.pages_window = value;
     else if (!strcmp(name, "mixed")) g_opt.mixed = value;
     else if (!strcmp(name, "l2_first")) g_opt.l2_first = value;
-    else if (!strcmp(name, "two")) g_opt.two = value;
+
     else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
     else if (!strcmp(name, "trace")) g_opt.trace = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
@@ -227,9 +228,11 @@ int set_kernel_attributes() {
                             (int)(kCompressSmemBytes + kMaxTableEntries * 2)));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#ifdef SB200_EXPERIMENTS
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#endif
     CU(cudaFuncSetAttribute(k_compress_pages_window<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_pages_window<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     // both window kernels share the SMs: ask for the full shared-memory carve-out so that the global-table
@@ -582,12 +585,14 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         // option `two`: the two-window round for the global-table warps (1), the shared-table warps (2), both (3)
         if (rules)
             k_compress_window_mixed<true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+#ifdef SB200_EXPERIMENTS  // measured slower (profiles/r02g_sweep_two_window.txt): 16.4 / 13.0 / 18.8 ms against 12.6 ms
         else if (c.opt.two == 1)
             k_compress_window_mixed<false, false, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         else if (c.opt.two == 2)
             k_compress_window_mixed<false, true, false><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         else if (c.opt.two == 3)
             k_compress_window_mixed<false, true, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+#endif
         else
             k_compress_window_mixed<false><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         *launches += 1;
@@ -1277,6 +1282,42 @@ namespace {
 //          it keeps the rule of the streamed compress path that everything a persistent kernel waits for is queued
 //          before that kernel;
 //   down : [copy device -> slot] a few pieces ahead, then parallel memcpy slot -> user on the calling thread.
+// One block of a big copy with non-temporal stores: the destination is either a pinned slot the DMA engine reads next
+// or the caller's result buffer, neither is read by this core soon, and a cached store would first fetch the line it
+// overwrites (a third of the copy's memory traffic).
+#if defined(__x86_64__)
+}  // namespace
+}  // extern "C++"
+#include <immintrin.h>
+extern "C++" {
+namespace {
+__attribute__((target("avx2"))) void stream_copy_avx2(u8* d, const u8* s, size_t n) {
+    while (n && (reinterpret_cast<uintptr_t>(d) & 31)) {
+        *d++ = *s++;
+        n--;
+    }
+    for (; n >= 128; n -= 128, s += 128, d += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 64));
+        const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 96), e);
+    }
+    if (n) memcpy(d, s, n);
+    _mm_sfence();
+}
+inline void block_copy(u8* d, const u8* s, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("SNAPPY_B200_NO_STREAM_COPY");
+    if (avx2) stream_copy_avx2(d, s, n);
+    else memcpy(d, s, n);
+}
+#else
+inline void block_copy(u8* d, const u8* s, size_t n) { memcpy(d, s, n); }
+#endif
+
 class CopyPool {  // a few persistent threads that split one memcpy among themselves (and the caller)
    public:
     static CopyPool& get() {
@@ -1319,7 +1360,7 @@ class CopyPool {  // a few persistent threads that split one memcpy among themse
         for (;;) {
             const size_t o = next_.fetch_add(kBlock);
             if (o >= n_) break;
-            memcpy(dst_ + o, src_ + o, n_ - o < kBlock ? n_ - o : kBlock);
+            block_copy(dst_ + o, src_ + o, n_ - o < kBlock ? n_ - o : kBlock);
         }
     }
     void loop() {

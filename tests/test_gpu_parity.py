@@ -298,7 +298,7 @@ def test_batched_shard_api(dev, oracle):
         assert np.array_equal(o.cpu().numpy(), streams[w][a:b])
 
 
-VARIANT_DEFAULTS = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6, "slowcont": 0, "lpt": 1}
+VARIANT_DEFAULTS = {"window": 1, "wide": 0, "l2_chains": 14, "smem_chains": 6, "slowcont": 0, "lpt": 1, "mixed": 1}
 
 
 def _variant_input():
@@ -312,6 +312,8 @@ def _variant_input():
     {"l2_chains": 0},       # window kernel, shared-memory tables only
     {"smem_chains": 0},     # window kernel, global tables only
     {"lpt": 0},             # fragments in stream order instead of expensive-first (schedule.cuh)
+    {"mixed": 0},           # the two table placements as two concurrent kernels (round 1) instead of one CTA
+    {"mixed": 2},           # one CTA, shared-table warps on the low warp numbers
 ])
 def test_compress_kernel_variants_bit_exact(dev, oracle, options):
     """every table placement / fragment order of the shipped compress kernel produces the oracle's bytes (the default
@@ -358,12 +360,13 @@ raw = _variant_input()
 want = pyoracle.compress_np(raw)
 d = torch.from_numpy(raw).cuda()
 bad = []
-for options in ({"window": 0}, {"wide": 4}, {"wide": 2}, {"slowcont": 1}, {"compress_variant": 1}, {"compress_variant": 2}):
+for options in ({"window": 0}, {"wide": 4}, {"wide": 2}, {"slowcont": 1}, {"compress_variant": 1}, {"compress_variant": 2},
+                {"two": 1}, {"two": 2}, {"two": 3}, {"mixed": 0}, {"mixed": 0, "l2_first": 1}):
     for k, v in options.items():
         dev.set_option(k, v)
     got = dev.compress_device(d)[0].cpu().numpy()
     for k in options:
-        dev.set_option(k, {"window": 1}.get(k, 0))
+        dev.set_option(k, {"window": 1, "mixed": 1}.get(k, 0))
     if got.size != want.size or not np.array_equal(got, want):
         bad.append(options)
 print("EXPERIMENTS_BAD", json.dumps(bad))
