@@ -70,7 +70,9 @@ __global__ void k_init_probe_offsets() {
 #define SB200_ST8(p, v) (*(p) = (u8)(v))
 #endif
 
-template <bool kSmemTable, bool kLib = false>
+// kSmemTable: 1 = the table lives in shared memory, 0 = in global memory (L2), 2 = either, decided per warp at run time
+// (dyn_smem): ONE copy of the round's code serves both kinds of warp of the merged kernel (instruction cache).
+template <int kSmemTable, bool kLib = false>
 struct Chain {
     static constexpr u32 kLitShort = kLib ? 61u : 60u;   // literals below this take the one-byte header (:271)
     static constexpr int kLimMargin = kLib ? 15 : 16;    // ip_limit = n - margin (:131)
@@ -82,21 +84,23 @@ struct Chain {
     u32 n, shift, lane, op, nrec, spec;  // spec: end positions pre-probed per copy (<= 32)
     int lim;
     u32 r_lit, r_cpy;  // lane k parks record k: (lit_from | ip << 16), (cand | M << 16)
+    bool dyn_smem;     // kSmemTable == 2 only
+    __device__ __forceinline__ bool in_smem() const { return kSmemTable == 2 ? dyn_smem : kSmemTable == 1; }
 
     __device__ __forceinline__ u32 hash(u32 w) const {
         return kLib ? (((w * kHashMul) >> shift) & hmask) : ((w * kHashMul) >> shift);
     }
 #ifdef SB200_CPU_EMU
     __device__ __forceinline__ u32 tget(u32 h) const {
-        return kSmemTable ? *reinterpret_cast<const u16*>(smem + Ts + 2u * h) : T[h];
+        return in_smem() ? *reinterpret_cast<const u16*>(smem + Ts + 2u * h) : T[h];
     }
     __device__ __forceinline__ void tput(u32 h, u32 pos) const {
-        if (kSmemTable) *reinterpret_cast<u16*>(smem + Ts + 2u * h) = (u16)pos;
+        if (in_smem()) *reinterpret_cast<u16*>(smem + Ts + 2u * h) = (u16)pos;
         else T[h] = (u16)pos;
     }
 #else
     __device__ __forceinline__ u32 tget(u32 h) const {
-        if (kSmemTable) {
+        if (in_smem()) {
             u16 v;
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(Ts + 2u * h) : "memory");
             return v;
@@ -108,7 +112,7 @@ struct Chain {
         return v;
     }
     __device__ __forceinline__ void tput(u32 h, u32 pos) const {
-        if (kSmemTable) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
+        if (in_smem()) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
         else asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; st.global.cg.L2::cache_hint.u16 [%0], %1, pol; }" ::"l"(T + h), "h"((u16)pos) : "memory");
     }
 #endif

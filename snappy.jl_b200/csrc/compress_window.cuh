@@ -32,6 +32,7 @@
 // (The two compile-time switches below are measured and decided; the dead arms stay because removing them
 // changed ptxas' schedule of the round for the worse: 26.1 vs 22.8 ms for the shared-table kernel.)
 #pragma once
+#include <type_traits>
 #include "compress_chain.cuh"
 
 namespace sb200 {
@@ -43,6 +44,9 @@ constexpr u32 kRingMirror = 32;  // the first bytes of the ring are repeated beh
 #define SB200_FAR_ALL 1
 #endif
 constexpr bool kFarAll = SB200_FAR_ALL != 0;
+#ifdef SB200_CPU_EMU_STATS
+static unsigned long g_emu_dist[17], g_emu_dist_hit[17];  // valid lanes by floor(log2(q - t)), and the hits among them
+#endif
 #ifdef SB200_CPU_EMU
 static unsigned long g_emu_rounds = 0, g_emu_second = 0;  // tools/cpu_warp: rounds run / second windows entered
 #endif
@@ -60,7 +64,7 @@ static unsigned long g_emu_rounds = 0, g_emu_second = 0;  // tools/cpu_warp: rou
 // changed since the round start is untrusted (entries only grow, so any insert with its hash shows), and the chain is
 // followed on.  The evaluation -- ring loads, hash, table lookup, candidate gather from L2 / DRAM, match length -- is
 // the latency-bound part of a round, and the two windows' loads overlap.  (tools/emulate_window.c WW=2 is the model.)
-template <bool kSmemTable, bool kLib = false, bool kSlowCont = false, bool kTwo = false>
+template <int kSmemTable, bool kLib = false, bool kSlowCont = false, bool kTwo = false>
 struct Win : Chain<kSmemTable, kLib> {
     using Base = Chain<kSmemTable, kLib>;
     using Base::F;
@@ -261,6 +265,15 @@ struct Win : Chain<kSmemTable, kLib> {
 #endif
             if (!V) m = 0;
         }
+#ifdef SB200_CPU_EMU_STATS  // tools/cpu_warp: how far back the candidates are, and how many of them are hits
+        if (V) {
+            const u32 dist = q - t;
+            u32 b = 0;
+            while ((1u << (b + 1)) <= dist && b < 16) b++;
+            g_emu_dist[b]++;
+            if (m >= 4u) g_emu_dist_hit[b]++;
+        }
+#endif
     }
 
     enum : u32 { K_COPY = 0, K_SLOW = 1, K_FIN = 2, K_NEXTSCAN = 3, K_NEXTARR = 4, K_LEAVE = 5 };
@@ -503,9 +516,12 @@ struct WindowArgs {
 // The life of one persistent warp: pull a fragment, clear the table, run the window rounds, record the size.
 //   T / ring : this warp's table (shared or global memory) and ring (shared-space address)
 //   kLib (option `rules`): libsnappy's rules, table sized per fragment; rules = 2: 64 KiB tables.
-template <bool kSmemTable, bool kLib, bool kSlowCont, bool kTwo = false>
+template <int kSmemTable, bool kLib>
+struct Pipe;  // compress_pipe.cuh: the same round with its loads one round ahead (kPipe)
+template <int kSmemTable, bool kLib, bool kSlowCont, bool kTwo = false, bool kPipe = false>
 __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u32 ring, u32 ring_bytes, u32 tab,
-                                                 u32 reserve) {
+                                                 u32 reserve, bool dyn_smem = false) {
+    const bool in_smem = kSmemTable == 2 ? dyn_smem : kSmemTable == 1;
     const u32 lane = lane_id();
     const u32 nfrag = A.nfrag;
     for (;;) {
@@ -552,11 +568,12 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
         uint4* t4 = reinterpret_cast<uint4*>(T);
         for (u32 i = lane; i < entries / 8; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        Win<kSmemTable, kLib, kSlowCont, kTwo> ch;
+        typename std::conditional<kPipe, Pipe<kSmemTable, kLib>, Win<kSmemTable, kLib, kSlowCont, kTwo>>::type ch;
         ch.hmask = entries - 1u;
         ch.F = (local == lastf) ? stail : sbase + start;
         ch.T = T;
-        ch.Ts = kSmemTable ? smem_u32(T) : 0u;
+        ch.Ts = in_smem ? smem_u32(T) : 0u;
+        ch.dyn_smem = dyn_smem;
         ch.out = A.scratch + (u64)frag * kSlotStride;
         ch.n = n;
         ch.shift = fshift;
@@ -568,7 +585,8 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
         ch.pre_at = 0xffffffffu;
         ch.nstage = (n + kRingChunk - 1u) & ~(kRingChunk - 1u);
         ch.aligned16 = (reinterpret_cast<uintptr_t>(ch.F) & 15u) == 0;
-        ch.run_window();
+        if constexpr (kPipe) ch.run_pipe();
+        else ch.run_window();
         if (lane == 0) A.frag_sizes[frag] = ch.op;
         if (A.trace && lane == 0) {  // option `trace`: [begin ns | table placement in bit 0, end ns | SM in the low 8 bits]
             u64 t_end = 0;
@@ -577,7 +595,7 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
 #endif
-            A.trace[2 * (u64)frag] = (t_begin & ~(u64)1) | (kSmemTable ? 1u : 0u);
+            A.trace[2 * (u64)frag] = (t_begin & ~(u64)1) | (in_smem ? 1u : 0u);
             A.trace[2 * (u64)frag + 1] = (t_end & ~(u64)0xff) | (smid & 0xffu);
         }
         if (A.done) {  // streamed output: per-chunk completion counts release the compaction of a chunk
@@ -591,7 +609,7 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
 
 // One table placement per launch: every warp of the CTA owns a table (behind each other in shared memory, or in
 // `gtables`) and `ring_bytes` of shared memory for its ring.  Used alone when the other placement is switched off.
-template <bool kSmemTable, bool kLib = false, bool kSlowCont = false>
+template <bool kSmemTable, bool kLib = false, bool kSlowCont = false, bool kPipe = false>
 __global__ void __launch_bounds__(kSmemTable ? 224 : 640, 1)
 k_compress_window(const WindowArgs A, u32 ring_bytes) {
     extern __shared__ __align__(128) u8 smem[];
@@ -601,7 +619,7 @@ k_compress_window(const WindowArgs A, u32 ring_bytes) {
     const u32 tab = kLib ? (A.lib_rules == 2u ? 2u * kMaxTableEntries : kMaxTableEntries) : kMaxTableEntries;
     u16* T = kSmemTable ? reinterpret_cast<u16*>(smem) + (size_t)warp * tab : A.gtables + (size_t)gwarp * tab;
     const u32 ring = smem_u32(smem) + (kSmemTable ? nwarp * tab * 2u : 0u) + warp * (ring_bytes + kRingMirror);
-    window_warp_loop<kSmemTable, kLib, kSlowCont>(A, T, ring, ring_bytes, tab, kSmemTable ? 0u : A.reserve);
+    window_warp_loop<kSmemTable, kLib, kSlowCont, false, kPipe>(A, T, ring, ring_bytes, tab, kSmemTable ? 0u : A.reserve);
 }
 
 // Both table placements in ONE CTA per SM (the default): warps [0, wb) keep their table in global memory (L2),
@@ -612,7 +630,10 @@ k_compress_window(const WindowArgs A, u32 ring_bytes) {
 // profiles/r02b_trace_fragments.txt).  One kernel is also what lets ncu measure the pair as it really runs.
 // Shared memory: wa tables, then wa rings of ring_a bytes, then wb rings of ring_b bytes.
 // kTwoA / kTwoB: the two-window round (Win<.., kTwo>) for the shared-table / global-table warps.
-template <bool kLib = false, bool kTwoA = false, bool kTwoB = false>
+// kPipe: bit 0 / bit 1 = the pipelined round (compress_pipe.cuh) for the shared-table / global-table warps.
+// kUni: ONE copy of the round's code for both kinds of warp (the table placement is a run-time flag of the warp): half
+// the instruction footprint of the hot loops, which is what the 32 KiB instruction cache of an SM sees.
+template <bool kLib = false, bool kTwoA = false, bool kTwoB = false, int kPipe = 0, bool kUni = false>
 __global__ void __launch_bounds__(640, 1)
 k_compress_window_mixed(const WindowArgs A, u32 wa, u32 wb, u32 ring_a, u32 ring_b, u32 smem_first) {
     extern __shared__ __align__(128) u8 smem[];
@@ -621,14 +642,23 @@ k_compress_window_mixed(const WindowArgs A, u32 wa, u32 wb, u32 ring_a, u32 ring
     const u32 rings = smem_u32(smem) + wa * tab * 2u;
     // smem_first (experiment): the shared-table warps take the LOW warp numbers instead
     const bool is_smem = smem_first ? warp < wa : warp >= wb;
+    if (kUni) {
+        const u32 w = is_smem ? (smem_first ? warp : warp - wb) : (smem_first ? warp - wa : warp);
+        u16* T = is_smem ? reinterpret_cast<u16*>(smem) + (size_t)w * tab : A.gtables + ((size_t)blockIdx.x * wb + w) * tab;
+        const u32 ring = is_smem ? rings + w * (ring_a + kRingMirror)
+                                 : rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror);
+        window_warp_loop<2, kLib, false, false, kPipe != 0>(A, T, ring, is_smem ? ring_a : ring_b, tab,
+                                                            is_smem ? 0u : A.reserve, is_smem);
+        return;
+    }
     if (is_smem) {
         const u32 w = smem_first ? warp : warp - wb;
         u16* T = reinterpret_cast<u16*>(smem) + (size_t)w * tab;
-        window_warp_loop<true, kLib, false, kTwoA>(A, T, rings + w * (ring_a + kRingMirror), ring_a, tab, 0u);
+        window_warp_loop<true, kLib, false, kTwoA, (kPipe & 1) != 0>(A, T, rings + w * (ring_a + kRingMirror), ring_a, tab, 0u);
     } else {
         const u32 w = smem_first ? warp - wa : warp;
         u16* T = A.gtables + ((size_t)blockIdx.x * wb + w) * tab;
-        window_warp_loop<false, kLib, false, kTwoB>(A, T, rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror),
+        window_warp_loop<false, kLib, false, kTwoB, (kPipe & 2) != 0>(A, T, rings + wa * (ring_a + kRingMirror) + w * (ring_b + kRingMirror),
                                                     ring_b, tab, A.reserve);
     }
 }

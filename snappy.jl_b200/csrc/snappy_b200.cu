@@ -21,7 +21,7 @@
 
 #include "compress.cuh"
 #include "compress_chain.cuh"
-#include "compress_window.cuh"
+#include "compress_pipe.cuh"
 #ifdef SB200_EXPERIMENTS
 #include "compress_wide.cuh"
 #endif
@@ -94,6 +94,8 @@ struct Options {
     int mixed = 1;              // 1 = both table placements in ONE kernel, shared-table warps on the high warp numbers;
                                 // 2 = the same with them on the low ones; 0 = two concurrent kernels (round 1)
     int two = 0;                // two-window round: 1 = global-table warps, 2 = shared-table warps, 3 = both (mixed kernel)
+    int pipe = 0;               // pipelined round (compress_pipe.cuh): 1 = shared-table warps, 2 = global-table warps, 3 = both
+    int unified = 0;            // merged kernel: one copy of the round's code for both table placements (run-time flag per warp)
     int l2_first = 0;           // mixed = 0 only: launch the global-table kernel before the shared-table kernel
     int pages_window = 1;       // batched pages <= 8 KiB: window-round kernel (0 = the serial page kernel for every size)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
@@ -179,6 +181,11 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "window")) g_opt.window = value;
     else if (!strcmp(name, "wide")) g_opt.wide = value;
     else if (!strcmp(name, "two")) g_opt.two = value;
+    else if (!strcmp(name, "pipe")) g_opt.pipe = value < 0 ? 0 : (value > 3 ? 3 : value);
+    else if (!strcmp(name, "unified")) g_opt.unified = value != 0;
+    else if (!strcmp(name, "l2_fetch")) {  // L2 fetch granularity in bytes (32, 64 or 128; the driver's default is 64): no effect measured
+        if (value == 32 || value == 64 || value == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value);
+    }
 #endif
     else if (!strcmp(name, "smem_chains")) g_opt.smem_chains = value < 0 ? 0 : (value > 7 ? 7 : value);
     else if (!strcmp(name, "l2_chains")) g_opt.l2_chains = value < 0 ? 0 : (value > 20 ? 20 : value);
@@ -229,6 +236,11 @@ int set_kernel_attributes() {
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #ifdef SB200_EXPERIMENTS
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window_mixed<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -243,6 +255,14 @@ int set_kernel_attributes() {
                             cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_compress_window<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
+#ifdef SB200_EXPERIMENTS
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_compress_window<true, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_compress_window<false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+#endif
     CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_compress_window<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -585,7 +605,20 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
         // option `two`: the two-window round for the global-table warps (1), the shared-table warps (2), both (3)
         if (rules)
             k_compress_window_mixed<true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
-#ifdef SB200_EXPERIMENTS  // measured slower (profiles/r02g_sweep_two_window.txt): 16.4 / 13.0 / 18.8 ms against 12.6 ms
+#ifdef SB200_EXPERIMENTS
+        // the pipelined round (compress_pipe.cuh) and the one-copy-of-the-code kernel: exact, measured, not faster
+        // (profiles/r02h_pipelined_round.md: the loads are hidden, but the round needs 33-40 % more instructions)
+        else if (c.opt.unified && c.opt.pipe)
+            k_compress_window_mixed<false, false, false, 3, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.unified)
+            k_compress_window_mixed<false, false, false, 0, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.pipe == 1)
+            k_compress_window_mixed<false, false, false, 1><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.pipe == 2)
+            k_compress_window_mixed<false, false, false, 2><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        else if (c.opt.pipe == 3)
+            k_compress_window_mixed<false, false, false, 3><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
+        // measured slower (profiles/r02g_sweep_two_window.txt): 16.4 / 13.0 / 18.8 ms against 12.6 ms
         else if (c.opt.two == 1)
             k_compress_window_mixed<false, false, true><<<grid, block, sm, st>>>(A, wa, wb, ra, rb, sf);
         else if (c.opt.two == 2)
@@ -629,6 +662,10 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter,
                 (u16*)c.gtables.p, (u32)c.opt.spec_l2, reserve, descs, ndesc);
 #endif
+#ifdef SB200_EXPERIMENTS
+        else if (c.opt.pipe & 2)
+            k_compress_window<false, false, false, true><<<ctas_b, wb * 32, smem_b, c.side>>>(A, rb);
+#endif
         else
             k_compress_window<false><<<ctas_b, wb * 32, smem_b, c.side>>>(A, rb);
         return SNAPPY_B200_OK;
@@ -647,6 +684,10 @@ int launch_chain_kernels(Context& c, const u8* d_in, size_t len, u32 shift, u8* 
             k_compress_chain<true><<<ctas_a, wa * 32, (size_t)wa * kMaxTableEntries * 2, st>>>(
                 d_in, (u64)len, nfrag, shift, (const u8*)c.tail.p, scratch, sizes, counter, nullptr,
                 (u32)c.opt.spec_smem, 0u, descs, ndesc);
+#endif
+#ifdef SB200_EXPERIMENTS
+        else if (c.opt.pipe & 1)
+            k_compress_window<true, false, false, true><<<ctas_a, wa * 32, smem_a, st>>>(A, ra);
 #endif
         else
             k_compress_window<true><<<ctas_a, wa * 32, smem_a, st>>>(A, ra);

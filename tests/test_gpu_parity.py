@@ -361,7 +361,8 @@ want = pyoracle.compress_np(raw)
 d = torch.from_numpy(raw).cuda()
 bad = []
 for options in ({"window": 0}, {"wide": 4}, {"wide": 2}, {"slowcont": 1}, {"compress_variant": 1}, {"compress_variant": 2},
-                {"two": 1}, {"two": 2}, {"two": 3}, {"mixed": 0}, {"mixed": 0, "l2_first": 1}):
+                {"two": 1}, {"two": 2}, {"two": 3}, {"mixed": 0}, {"mixed": 0, "l2_first": 1},
+                {"pipe": 1}, {"pipe": 2}, {"pipe": 3}, {"unified": 1}, {"unified": 1, "pipe": 3}, {"pipe": 3, "mixed": 0}):
     for k, v in options.items():
         dev.set_option(k, v)
     got = dev.compress_device(d)[0].cpu().numpy()

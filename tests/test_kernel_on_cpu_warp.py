@@ -26,9 +26,9 @@ def warp(tmp_path_factory):
     return exe
 
 
-def run(exe, files, table, rules, ring, kernel="window", slowcont=0, mixed=0, two=0):
+def run(exe, files, table, rules, ring, kernel="window", slowcont=0, mixed=0, two=0, pipe=0, uni=0):
     env = dict(os.environ, TABLE=table, RULES=str(rules), RING=str(ring), KERNEL=kernel, SLOWCONT=str(slowcont),
-               MIXED=str(mixed), TWO=str(two))
+               MIXED=str(mixed), TWO=str(two), PIPE=str(pipe), UNI=str(uni))
     p = subprocess.run([exe] + files, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     lines = [l for l in p.stdout.splitlines() if "fragments" in l]
@@ -68,6 +68,26 @@ def test_two_window_round_source_matches_oracle(warp, table, ring, tmp_path):
         p.write_bytes(b)
         files.append(str(p))
     run(warp, files, table, 0, ring, mixed=1, two=1)
+
+
+@pytest.mark.parametrize("table,ring,pipe,uni", [("smem", 2048, 1, 0), ("global", 1024, 1, 0), ("global", 1024, 0, 1),
+                                                 ("smem", 2048, 1, 1)])
+def test_pipelined_round_and_shared_code_sources_match_oracle(warp, table, ring, pipe, uni, tmp_path):
+    """options `pipe` (compress_pipe.cuh: the round's loads issued one round ahead, validated by re-reading the table
+    entry) and `unified` (one copy of the round's code, table placement per warp at run time): experiments, exact"""
+    run(warp, [os.path.join(DATA, f) for f in FILES + ["urls.10K", "kppkn.gtb"]], table, 0, ring, mixed=1, pipe=pipe, uni=uni)
+    rng = np.random.default_rng(6)
+    blobs = [bytes(rng.integers(0, 3, 70000, dtype=np.uint8)), b"ab" * 40000, b"\0" * 66000,
+             (b"0123456789abcdef" * 5 + b"X") * 900, bytes(rng.integers(97, 101, 200000, dtype=np.uint8)),
+             b"".join(bytes([65 + (i * 7) % 23]) * (1 + i % 40) for i in range(4000))]
+    text = b" ".join(bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(30000))
+    blobs += [text[:n] for n in (15, 16, 17, 47, 48, 49, 63, 64, 65, 79, 80, 81, 95, 96, 97, 4096, 65535, 65536, 65537)]
+    files = []
+    for i, b in enumerate(blobs):
+        p = tmp_path / ("p%02d.bin" % i)
+        p.write_bytes(b)
+        files.append(str(p))
+    run(warp, files, table, 0, ring, mixed=1, pipe=pipe, uni=uni)
 
 
 def test_kernel_source_on_boundary_sizes_and_patterns(warp, tmp_path):

@@ -5,7 +5,7 @@
 //
 //   g++ -O1 -std=c++17 -DSB200_CPU_EMU -Itools/cpu_warp tools/cpu_warp/run_window_kernel.cpp oracle/snappy_oracle.c
 //   TABLE=smem|global RULES=0|1|2 RING=2048 KERNEL=window|chain SLOWCONT=0|1 ./a.out file...
-#include "../../snappy.jl_b200/csrc/compress_window.cuh"
+#include "../../snappy.jl_b200/csrc/compress_pipe.cuh"
 
 extern "C" {
 #include "../../oracle/snappy_oracle.h"
@@ -31,6 +31,7 @@ struct Args {
     bool slowcont;  // SLOWCONT=1: the experimental window variant (option slowcont), rules 0 only
     bool mixed;     // MIXED=1: k_compress_window_mixed (one CTA holds both table placements)
     bool two;       // TWO=1 (with MIXED=1, rules 0): the two-window round
+    bool pipe;      // PIPE=1 (with MIXED=1): the pipelined round (compress_pipe.cuh)
 };
 
 static WindowArgs wargs(const Args& a) {
@@ -53,7 +54,11 @@ template <bool kSmem, bool kLib>
 static void launch(const Args& a) {
     if (a.mixed) {  // the default launch form: both placements in one CTA; this warp plays the role TABLE names
         // CTA of wb = 1 global-table warp and wa = 1 shared-table warp: warp 0 / warp 1 (the harness sets tid_base)
-        if (a.two && !kLib) k_compress_window_mixed<false, true, true>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        if (getenv("UNI") && atoi(getenv("UNI")) && !kLib) {
+            if (a.pipe) k_compress_window_mixed<false, false, false, 3, true>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+            else k_compress_window_mixed<false, false, false, 0, true>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        } else if (a.pipe) k_compress_window_mixed<kLib, false, false, 3>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
+        else if (a.two && !kLib) k_compress_window_mixed<false, true, true>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
         else k_compress_window_mixed<kLib>(wargs(a), 1u, 1u, a.ring, a.ring, 0u);
         return;
     }
@@ -91,6 +96,7 @@ int main(int argc, char** argv) {
     const bool slowcont = getenv("SLOWCONT") && atoi(getenv("SLOWCONT")) != 0;
     const bool mixed = getenv("MIXED") && atoi(getenv("MIXED")) != 0;
     const bool two = getenv("TWO") && atoi(getenv("TWO")) != 0;
+    const bool pipe = getenv("PIPE") && atoi(getenv("PIPE")) != 0;
     if ((chain || slowcont) && rules) {
         fprintf(stderr, "KERNEL=chain has no rules instantiation\n");
         return 2;
@@ -126,7 +132,7 @@ int main(int argc, char** argv) {
         u32 counter = 0;
         u32 entries = sjo_hashtable_entries((u64)sz), shift = 32;
         for (u32 e = entries; e > 1; e >>= 1) shift--;
-        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont, mixed, two};
+        Args a{smem_table, in, (u64)sz, nfrag, shift, tail, scratch, sizes, &counter, gtables, ring, rules, chain, slowcont, mixed, two, pipe};
         cpu_warp::W().collectives = 0;
         if (mixed) {  // CTA of two warps: warp 0 = global-table role, warp 1 = shared-table role
             cpu_warp::W().block = 0;
@@ -154,8 +160,27 @@ int main(int argc, char** argv) {
                 if (bad++ < 3) fprintf(stderr, "%s: fragment %u differs (%u vs %zu bytes)\n", argv[ai], f, sizes[f], c);
             }
         }
-        if (getenv("ROUNDS")) printf("rounds %lu, second windows entered %lu\n", sb200::g_emu_rounds, sb200::g_emu_second);
+        if (getenv("ROUNDS")) {
+            printf("rounds %lu, second windows entered %lu\n", sb200::g_emu_rounds, sb200::g_emu_second);
+            if (pipe)
+                printf("pipelined rounds %lu: %lu cold, %lu with re-evaluated lanes, mean window %.1f\n", sb200::g_emu_pipe_rounds,
+                       sb200::g_emu_pipe_cold, sb200::g_emu_pipe_fix, (double)sb200::g_emu_pipe_w / (double)(sb200::g_emu_pipe_rounds ? sb200::g_emu_pipe_rounds : 1));
+        }
+#ifdef SB200_CPU_EMU_STATS
+        {
+            unsigned long all = 0, hits = 0, cum = 0;
+            for (int b = 0; b < 17; b++) all += sb200::g_emu_dist[b], hits += sb200::g_emu_dist_hit[b];
+            printf("valid lanes %lu, hits %lu (%.1f %%); cumulative share of candidates closer than 2^k:", all, hits, 100.0 * hits / (all ? all : 1));
+            for (int b = 0; b < 17; b++) {
+                cum += sb200::g_emu_dist[b];
+                if (b >= 8) printf(" %d:%.0f%%", b + 1, 100.0 * cum / (all ? all : 1));
+                sb200::g_emu_dist[b] = sb200::g_emu_dist_hit[b] = 0;
+            }
+            printf("\n");
+        }
+#endif
         sb200::g_emu_rounds = sb200::g_emu_second = 0;
+        sb200::g_emu_pipe_rounds = sb200::g_emu_pipe_cold = sb200::g_emu_pipe_fix = sb200::g_emu_pipe_w = 0;
         printf("%s: %u fragments, %ld mismatches (%s kernel, %s table, rules %u, ring %u, %llu collectives)\n", argv[ai], nfrag, bad,
                chain ? "chain" : (slowcont ? "window+slowcont" : "window"), smem_table ? "shared" : "global", rules, ring, (unsigned long long)cpu_warp::W().collectives);
         failed += bad != 0;
