@@ -179,6 +179,14 @@ constexpr u32 kDecodeWarpsPerCta = 2;   // small CTAs: finished warps free their
 // unfinished element; long elements are copied by the whole warp when they become the first
 // unfinished one (incremental_copy! / copy_literal!, src/internal.jl:477-527).
 constexpr u32 kShortElem = 16;
+// The window walk reads the stream front to back, 30-100 bytes per window, and 8 % of the decoder's warp time sits on
+// the first use of a window's tag words (profiles/r02q_prof_decode.txt).  Build switch: one lane asks for the line
+// kDecodePrefetch bytes ahead.  Measured 0 / 256 / 512 / 1024 bytes ahead into L2, 512 into L1: 4.78 / 4.79 / 4.71 /
+// 4.78 / 4.79 ms per GiB (profiles/r02r_decode_variants.txt): within noise, so off.
+#ifndef SB200_DECODE_PREFETCH
+#define SB200_DECODE_PREFETCH 0
+#endif
+constexpr u32 kDecodePrefetch = SB200_DECODE_PREFETCH;
 
 // branch-free form of decode_tag for the window parse (same fields; CHAR_TABLE / WORDMASK of
 // src/internal.jl:47-85 evaluated arithmetically)
@@ -204,6 +212,14 @@ __device__ __forceinline__ bool decode_fast_warp(const u8* __restrict__ in, u64 
         const u32 p = base + lane;
         const bool inb = p < nin;
         const u32 rem = inb ? nin - p : 1u;  // bytes from p to the end of the run (>= 1)
+#ifndef SB200_CPU_EMU
+        if (kDecodePrefetch && lane == 0 && base + kDecodePrefetch < nin)
+#ifdef SB200_DECODE_PREFETCH_L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(src + base + kDecodePrefetch));
+#else
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + base + kDecodePrefetch));
+#endif
+#endif
         u32 c = 0, tag4 = 0;
         if (inb) {
             if (rem >= 12) {
