@@ -292,6 +292,143 @@ k_build_index(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
     if (straddle) atomicOr(&pa.counters[0], PF_STRADDLE);
 }
 
+// ---- clean cuts: tiles for streams whose copies reach across the 64 KiB output boundaries ------------------------
+// An element start at output position p is a CLEAN CUT iff no element at or behind p reads output below p: then
+// everything from p on can be decoded without what lies before it.  With reach(e) = op(e) - offset(e) for a copy e
+// and R(p) = min reach over the copies at positions >= p (a suffix minimum, so R only falls as p falls):
+// p is clean iff R(p) >= p, and if it is not, every cut in (R(p), p] is unclean as well (its suffix contains the
+// same low copy).  So the greatest clean cut at or below a boundary B is found by jumping back: p = greatest element
+// start <= B; while R(p) < p: p = greatest element start <= R(p).  It ends at p = 0 at the latest.
+// Tile f of the re-tiled index starts at the greatest clean cut <= f * 65536 (monotone in f; a tile may be empty,
+// its neighbour then spans more than 64 KiB), so a stream made of blocks that do not tile 64 KiB -- or one with a few
+// long-range copies -- still decodes tile-parallel; only a stream whose copies chain across every boundary ends up
+// as one long tile on one warp.
+constexpr u32 kCutIters = 256;
+constexpr u64 kCutNone = ~0ull - 1ull;
+
+// low[k] = min reach of the copies that start in chunk k (~0: none)
+__global__ void __launch_bounds__(kParseThreads)
+k_cut_low(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, const u64* __restrict__ out_off,
+          u64 E, u32 pshift, u64* __restrict__ low) {
+    const u32 k = blockIdx.x * kParseThreads + threadIdx.x;
+    if (k >= nchunk) return;
+    u64 m = ~0ull;
+    u64 ip = pa.entry[k];
+    if (ip != kDeadPos) {
+        u64 start, end;
+        chunk_range(hdr, E, k, pshift, start, end);
+        u64 op = out_off[k];
+        Element e;
+        while (ip < end && ip + 1 < L) {
+            if (!walk_step(in, L, ip, e)) break;
+            if (e.is_copy) {
+                const u64 r = (u64)e.offset <= op ? op - e.offset : 0;
+                m = r < m ? r : m;
+            }
+            op += e.len;
+        }
+    }
+    low[k] = m;
+}
+
+// sfx[k] = min(low[k + 1 ..]) (one CTA, from the end)
+__global__ void __launch_bounds__(1024)
+k_suffix_min(const u64* __restrict__ low, u32 n, u64* __restrict__ sfx) {
+    __shared__ u64 warp_min[32];
+    __shared__ u64 carry_s;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = ~0ull;
+    __syncthreads();
+    for (u32 done = 0; done < n; done += 1024) {
+        // thread t takes element i = n - 1 - (done + t): an inclusive scan over t is a suffix minimum over i
+        const u32 t = done + tid;
+        const bool in_range = t < n;
+        const u32 i = in_range ? n - 1 - t : 0;
+        const u64 v = in_range ? low[i] : ~0ull;
+        u64 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 o = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= (u32)d) incl = o < incl ? o : incl;
+        }
+        if (lane == 31) warp_min[wid] = incl;
+        __syncthreads();
+        u64 before = carry_s, total = carry_s;
+#pragma unroll
+        for (u32 w = 0; w < 32; w++) {
+            if (w < wid) before = warp_min[w] < before ? warp_min[w] : before;
+            total = warp_min[w] < total ? warp_min[w] : total;
+        }
+        // exclusive: everything behind i, i.e. the threads before t and the blocks before this one
+        const u64 up = __shfl_up_sync(kFullMask, incl, 1);
+        u64 excl = before;
+        if (lane > 0) excl = up < excl ? up : excl;
+        if (in_range) sfx[i] = excl;
+        __syncthreads();
+        if (tid == 0) carry_s = total;
+        __syncthreads();
+    }
+}
+
+// one thread per tile f in [1, nfrag): the greatest clean cut <= f * 65536 (kCutNone: gave up, k_cut_fill decides)
+__global__ void __launch_bounds__(kParseThreads)
+k_cut_tiles(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays pa, const u64* __restrict__ out_off,
+            const u64* __restrict__ sfx, u64 E, u32 pshift, u32 nfrag, u64* __restrict__ index,
+            u64* __restrict__ out_start) {
+    const u32 f = 1 + blockIdx.x * kParseThreads + threadIdx.x;
+    if (f >= nfrag) return;
+    u64 x = (u64)f << 16;
+    for (u32 iter = 0; iter < kCutIters; iter++) {
+        // the chunk whose elements cover output byte x: out_off[k] <= x < out_off[k + 1]
+        u32 lo = 0, hi = nchunk;  // invariant: out_off[lo] <= x, out_off[hi] > x (out_off[nchunk] = total > x)
+        while (hi - lo > 1) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (out_off[mid] <= x) lo = mid;
+            else hi = mid;
+        }
+        const u32 k = lo;
+        u64 ip = pa.entry[k];
+        if (ip == kDeadPos) break;  // cannot happen for a complete parse (the covering chunk has output)
+        u64 start, end;
+        chunk_range(hdr, E, k, pshift, start, end);
+        u64 op = out_off[k], p_op = op, p_ip = ip, m = ~0ull;
+        Element e;
+        while (ip < end && ip + 1 < L) {
+            const u64 at = ip;
+            if (!walk_step(in, L, ip, e)) break;
+            if (op <= x) {  // a later element start at or below x: the suffix starts again here
+                p_op = op;
+                p_ip = at;
+                m = ~0ull;
+            }
+            if (e.is_copy) {
+                const u64 r = (u64)e.offset <= op ? op - e.offset : 0;
+                m = r < m ? r : m;
+            }
+            op += e.len;
+        }
+        const u64 s = sfx[k];
+        const u64 R = s < m ? s : m;
+        if (R >= p_op) {
+            index[f] = p_ip;
+            out_start[f] = p_op;
+            return;
+        }
+        x = R;
+    }
+    out_start[f] = kCutNone;
+}
+
+// tiles that gave up take their predecessor's start: the predecessor becomes empty, this tile spans both
+__global__ void k_cut_fill(u32 nfrag, u64* __restrict__ index, u64* __restrict__ out_start) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (u32 f = 1; f < nfrag; f++)
+        if (out_start[f] == kCutNone) {
+            out_start[f] = out_start[f - 1];
+            index[f] = index[f - 1];
+        }
+}
+
 // first tile whose index entry was never written (the chain broke before it): everything below is trustworthy
 __global__ void __launch_bounds__(256)
 k_first_missing(const u64* __restrict__ index, u32 nfrag, u64 L, u32* __restrict__ first) {

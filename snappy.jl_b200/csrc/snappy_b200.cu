@@ -99,6 +99,7 @@ struct Options {
     int l2_first = 0;           // mixed = 0 only: launch the global-table kernel before the shared-table kernel
     int pages_window = 1;       // batched pages <= 8 KiB: window-round kernel (0 = the serial page kernel for every size)
     int lpt = 1;                // compress: order the fragments by estimated cost, expensive first (k_estimate_cost)
+    int clean_cuts = 1;         // index-free decode: re-tile at clean cuts when copies cross the 64 KiB boundaries (0: bounded serial walk only)
     int pin_host = 1;           // host-buffer API on pageable memory: register the caller's buffers for the call
 };
 
@@ -120,7 +121,7 @@ struct Context {
     cudaEvent_t ev_in[kMaxPipeChunks] = {}, ev_done[kMaxPipeChunks] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch for decode
-    DevBuf result, parse_a, parse_b, parse_c, index, index_out, tile_flags;
+    DevBuf result, parse_a, parse_b, parse_c, parse_d, index, index_out, tile_flags;
     // staging for the host-buffer API
     DevBuf stage_in, stage_out;
     void* pinned = nullptr;  // small pinned readback area (kPinnedBytes)
@@ -225,6 +226,7 @@ void apply_option(const char* name, int value) {
     else if (!strcmp(name, "profile_range")) g_opt.profile_range = value;
     else if (!strcmp(name, "trace")) g_opt.trace = value;
     else if (!strcmp(name, "pin_host")) g_opt.pin_host = value;
+    else if (!strcmp(name, "clean_cuts")) g_opt.clean_cuts = value != 0;
 }
 
 // Shared-memory opt-ins of the kernels (per device; the attributes live in the device's module).
@@ -412,7 +414,7 @@ void ctx_destroy(Context& c) {
     if (c.ev_join) cudaEventDestroy(c.ev_join);
     c.ev_fork = c.ev_join = nullptr;
     for (DevBuf* b : {&c.descs, &c.tail, &c.gtables, &c.scratch, &c.frag_sizes, &c.frag_offsets, &c.result, &c.parse_a,
-                      &c.parse_b, &c.parse_c, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order, &c.trace, &c.index_out, &c.tile_flags})
+                      &c.parse_b, &c.parse_c, &c.parse_d, &c.index, &c.stage_in, &c.stage_out, &c.flags, &c.order, &c.trace, &c.index_out, &c.tile_flags})
         b->release();
     if (c.pinned) cudaFreeHost(c.pinned);
     if (c.pinned_zero) cudaFreeHost(c.pinned_zero);
@@ -1056,6 +1058,28 @@ int decode_parsed_locked(Context& c, const u8* d_in, size_t n, size_t hdr, u8* d
     }
     CU(cudaMemcpyAsync(ost + nfrag, hseed + 2, 8, cudaMemcpyHostToDevice, st));
     const bool complete = !(pflags & (PF_ANOMALY | PF_BROKEN)) && total == claimed;
+    if (complete && (pflags & PF_NOT_CLEAN) && nfrag > 1 && c.opt.clean_cuts) {
+        // copies reach across the 64 KiB boundaries: move every tile start back to the nearest clean cut (parse.cuh),
+        // so that the tiles are self-contained again wherever the stream allows it.  The parse arrays of
+        // build_index_segment (entries, output offsets per chunk) are still in place.
+        const u32 pshift = (u32)c.opt.parse_chunk_log2;
+        const u64 pchunk = 1ull << pshift;
+        const u32 nchunk = (u32)(((u64)(n - hdr) + pchunk - 1) / pchunk);
+        ParseArrays pa;
+        pa.carve(c.parse_a.p, nchunk);
+        const u64* out_off = (const u64*)c.parse_c.p;
+        CU(c.parse_d.ensure((size_t)nchunk * 16));
+        u64* low = (u64*)c.parse_d.p;
+        u64* sfx = low + nchunk;
+        const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
+        k_cut_low<<<pgrid, kParseThreads, 0, st>>>(d_in, (u64)n, (u64)hdr, nchunk, pa, out_off, (u64)n, pshift, low);
+        k_suffix_min<<<1, 1024, 0, st>>>(low, nchunk, sfx);
+        k_cut_tiles<<<(nfrag - 1 + kParseThreads - 1) / kParseThreads, kParseThreads, 0, st>>>(
+            d_in, (u64)n, (u64)hdr, nchunk, pa, out_off, sfx, (u64)n, pshift, nfrag, idx, ost);
+        k_cut_fill<<<1, 32, 0, st>>>(nfrag, idx, ost);
+        c.last_launches[1] += 4;
+        CU(cudaGetLastError());
+    }
     u32 tvalid = nfrag;  // tiles [0, tvalid) have both ends in the index
     if (!complete) {
         u32* d_first = (u32*)((u8*)c.result.p + 128);
@@ -2401,7 +2425,7 @@ int snappy_b200_get_option(const char* name) {
         {"parse_chunk_log2", o.parse_chunk_log2}, {"uncompress_segments", o.uncompress_segments},
         {"host_pipeline", o.host_pipeline}, {"timing", o.timing}, {"l2_persist", o.l2_persist},
         {"overlap_compact", o.overlap_compact}, {"window", o.window}, {"wide", o.wide}, {"slowcont", o.slowcont},
-        {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host}, {"trace", o.trace},
+        {"compress_variant", o.compress_variant}, {"lpt", o.lpt}, {"pin_host", o.pin_host}, {"clean_cuts", o.clean_cuts}, {"trace", o.trace},
         {"profile_range", o.profile_range}, {"pages_window", o.pages_window}, {"mixed", o.mixed}, {"l2_first", o.l2_first}, {"two", o.two},
     };
     for (const auto& e : tab)

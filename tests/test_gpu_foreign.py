@@ -50,11 +50,87 @@ def test_block_structured_foreign_streams(snappy, oracle, block):
     raw = synth.mix(48, seed=17, tail=4321)
     stream = _blocky_stream(oracle, raw, block)
     assert oracle.uncompress_np(stream).tobytes() == raw.tobytes()
-    got = device.uncompress_device(torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).cuda())
+    d = torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).cuda()
+    got = device.uncompress_device(d)
     assert np.array_equal(got.cpu().numpy(), raw)
-    # blocks that tile the 64 KiB boundaries decode fully in parallel; the others need the bounded serial walk for
-    # the tiles a copy reaches out of -- but never the whole-stream serial decoder
-    assert _path(snappy) == (1 if 65536 % block == 0 else 2)
+    # every block size decodes tile-parallel: where the blocks do not tile 64 KiB the tiles start at the nearest clean
+    # cut (an element start no later copy reaches across, parse.cuh) instead of on the boundary
+    assert _path(snappy) == 1
+    # without the clean cuts the tiles a copy reaches out of go to the bounded serial walk -- never to the
+    # whole-stream serial decoder -- and the bytes are the same
+    device.set_option("clean_cuts", 0)
+    try:
+        got = device.uncompress_device(d)
+        assert np.array_equal(got.cpu().numpy(), raw)
+        assert _path(snappy) == (1 if 65536 % block == 0 else 2)
+    finally:
+        device.set_option("clean_cuts", 1)
+
+
+def _lit(data):
+    n = len(data)
+    assert 60 < n <= 1 << 24
+    return bytes([62 << 2]) + (n - 1).to_bytes(3, "little") + data     # literal, 3 length bytes
+
+
+def _copy4(length, offset):
+    assert 1 <= length <= 64
+    return bytes([((length - 1) << 2) | 3]) + offset.to_bytes(4, "little")  # copy with a 4-byte offset
+
+
+def test_long_range_copies_keep_the_rest_tile_parallel(snappy, oracle):
+    """a hand-made stream whose copies use 4-byte offsets and reach hundreds of KiB back (no compressor in this repo
+    emits them; the format allows them, src/internal.jl:28-30): the tiles around such a copy merge into one that
+    begins at the clean cut below the copy's source, everything else stays 64 KiB-parallel; also a copy chain that
+    leaves no clean cut at all (one tile = the whole stream), and an offset that reaches before the stream"""
+    import torch
+    from snappy_jl_b200 import device
+    rng = np.random.default_rng(99)
+    parts, raw = [], bytearray()
+
+    def lit(n):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        parts.append(_lit(b))
+        raw.extend(b)
+
+    def cp(length, offset):
+        parts.append(_copy4(length, offset))
+        for _ in range(length):
+            raw.append(raw[-offset])
+
+    for i in range(24):
+        lit(50000 + 977 * i)
+        if i in (5, 6, 17):
+            cp(64, 300000 + i)       # far back, across several tiles
+        if i == 11:
+            cp(40, 70000)
+            cp(64, 131072)
+    body = b"".join(parts)
+    stream = np.frombuffer(oracle.encode32(len(raw)) + body, dtype=np.uint8).copy()
+    want = np.frombuffer(bytes(raw), dtype=np.uint8)
+    assert np.array_equal(oracle.uncompress_np(stream), want)
+    got = device.uncompress_device(torch.from_numpy(stream).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert _path(snappy) == 1
+    assert snappy.uncompress(stream.tobytes()) == bytes(raw)            # host-buffer API
+    # every tile reaches into its predecessor: no clean cut but 0 -- still correct (one long tile)
+    parts, raw = [], bytearray()
+    lit(70000)
+    for i in range(40):
+        lit(30000)
+        cp(64, 65000)
+    stream = np.frombuffer(oracle.encode32(len(raw)) + b"".join(parts), dtype=np.uint8).copy()
+    want = np.frombuffer(bytes(raw), dtype=np.uint8)
+    assert np.array_equal(oracle.uncompress_np(stream), want)
+    got = device.uncompress_device(torch.from_numpy(stream).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    # an offset that reaches before the first byte: the reference's status (src/internal.jl:499)
+    bad = np.frombuffer(oracle.encode32(70064) + _lit(bytes(70000)) + _copy4(64, 70001), dtype=np.uint8).copy()
+    want_status = oracle.status_of_uncompress(bad)
+    assert want_status != 0
+    with pytest.raises(snappy.SnappyError) as e:
+        device.uncompress_device(torch.from_numpy(bad).cuda())
+    assert e.value.status == want_status
 
 
 def test_corrupt_256_mib_stream_is_rejected_fast_with_the_reference_status(snappy, oracle):
