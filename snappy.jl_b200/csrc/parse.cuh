@@ -40,11 +40,18 @@
 namespace sb200 {
 
 constexpr u32 kParseChunkLog2 = 10;   // default: 1 KiB of compressed bytes per chunk (one thread each)
-constexpr u32 kParseLookback = 1024;  // guess walk starts this far before the chunk
+#ifndef SB200_PARSE_LOOKBACK
+#define SB200_PARSE_LOOKBACK 256
+#endif
+// guess walk starts this far before the chunk (1024 / 512 / 256: 8.22 / 7.85 / 7.67 ms per step of config 3,
+// profiles/r02u_parse_lookback.txt; a guess that has not joined the real chain by the chunk start costs a bridge walk,
+// never a wrong result)
+constexpr u32 kParseLookback = SB200_PARSE_LOOKBACK;
 constexpr u32 kParseThreads = 128;
 constexpr u32 kBridgeBudget = 20000;  // elements a bridge may walk before it gives up
 constexpr u64 kDeadPos = ~0ull;
 constexpr u32 kNextDead = 0xffffffffu;  // chain cannot be followed from here
+constexpr u32 kOutbUnknown = 0xffffffffu;  // outb[] after the guess pass: the walk failed
 
 enum : u32 { PF_ANOMALY = 1u, PF_NOT_CLEAN = 2u, PF_BROKEN = 4u, PF_STRADDLE = 8u };
 
@@ -126,6 +133,9 @@ k_parse_guess(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
     const bool ok = walk_chunk(in, L, end, ip, produced);
     pa.exit[k] = ok ? ip : kDeadPos;
     pa.reach[k] = (k == 0) ? 1u : 0u;
+    // output bytes of the chunk as walked from the guess: k_parse_final keeps them when the guess turns out to be the
+    // chunk's real entry (nearly always), instead of walking the chunk once more
+    pa.outb[k] = (ok && produced <= 0xfffffffeull) ? (u32)produced : kOutbUnknown;
 }
 
 __global__ void __launch_bounds__(kParseThreads)
@@ -203,6 +213,7 @@ k_parse_final(const u8* __restrict__ in, u64 L, u64 hdr, u32 nchunk, ParseArrays
     if (k >= nchunk) return;
     u64 ip = pa.entry[k];
     u64 produced = 0;
+    if (ip != kDeadPos && ip == pa.first[k] && pa.outb[k] != kOutbUnknown) return;  // the guess pass walked exactly this
     if (ip != kDeadPos) {
         u64 start, end;
         chunk_range(hdr, E, k, pshift, start, end);
