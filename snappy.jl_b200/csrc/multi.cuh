@@ -75,10 +75,15 @@ k_scan_shards(const u32* __restrict__ sizes, const AsmDesc* __restrict__ descs, 
 // one CTA per fragment: the fragment's bytes from its scratch slot to header + (bytes of the ranks before) + (offset
 // inside the segment) in the owner's stream region; destination-aligned 16-byte stores (as k_compact), which cross
 // NVLink when the owner is another GPU.  Thread 0 also stores the fragment's stream offset into the owner's index.
+// `rot`: CTAs are handed out in blockIdx order, i.e. stream after stream; every rank starts with a DIFFERENT stream
+// (the one behind its own), so that at any moment the N ranks store into N different owners.  In stream order all of
+// them wrote to owner 0 first, then owner 1, ...: one GPU's NVLink ingress at a time (measured at N = 8: 2.2-2.4 ms
+// for 0.42 GB per rank, profiles/r02v_trace_n8.txt).
 __global__ void __launch_bounds__(256)
 k_assemble(const u8* __restrict__ scratch, const u32* __restrict__ sizes, const u64* __restrict__ rel,
-           const u64* __restrict__ M, u32 nstreams, const AsmDesc* __restrict__ descs, u32 ndesc) {
-    const u32 frag = blockIdx.x;
+           const u64* __restrict__ M, u32 nstreams, const AsmDesc* __restrict__ descs, u32 ndesc, u32 rot) {
+    u32 frag = blockIdx.x + rot;
+    if (frag >= gridDim.x) frag -= gridDim.x;
     u32 k = 0;
     while (k + 1 < ndesc && descs[k + 1].frag_begin <= frag) k++;
     const AsmDesc d = descs[k];
