@@ -181,6 +181,71 @@ def test_exact_decoder_source_matches_oracle_statuses(decode_warp, oracle, tmp_p
 
 
 # ---------------------------------------------------------------------------------------------- the index-free parse
+def test_clean_cut_retiling_matches_brute_force(oracle, tmp_path):
+    """parse.cuh k_cut_low / k_cut_tiles / k_cut_fill (the re-tiling decode_parsed_locked runs when copies cross the
+    64 KiB output boundaries): tile f must start at the greatest element start <= f * 65536 that no later copy reaches
+    across -- block sizes that do and do not tile 64 KiB, hand-made 4-byte-offset copies hundreds of KiB back, a copy
+    chain that leaves no clean cut but 0, the reference's foreign fixture, and ordinary streams (every boundary clean)"""
+    from conftest import read_data
+    from snappy_jl_b200 import synth
+    exe = str(tmp_path / "run_parse_kernel")
+    obj = str(tmp_path / "oracle.o")
+    subprocess.check_call(["gcc", "-O2", "-c", "-o", obj, os.path.join(ROOT, "oracle", "snappy_oracle.c")])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DSB200_CPU_EMU", "-I" + os.path.join(ROOT, "tools", "cpu_warp"),
+                           "-o", exe, os.path.join(ROOT, "tools", "cpu_warp", "run_parse_kernel.cpp"), obj])
+    raw = synth.mix(12, seed=17, tail=4321)
+    files = []
+
+    def put(name, data):
+        p = tmp_path / name
+        p.write_bytes(data)
+        files.append(str(p))
+
+    for block in (50000, 7777, 32768, 65536, 100000, 1000):
+        parts = [oracle.encode32(raw.size)]
+        for o in range(0, raw.size, block):
+            s = oracle.compress(raw[o: o + block].tobytes())
+            _, k = oracle.parse32(s, 0)
+            parts.append(s[k:])
+        put("blocky_%d.snappy" % block, b"".join(parts))
+    rng = np.random.default_rng(99)
+
+    def lit(parts, out, n):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        parts.append(bytes([62 << 2]) + (n - 1).to_bytes(3, "little") + b)
+        out.extend(b)
+
+    def cp(parts, out, length, offset):
+        parts.append(bytes([((length - 1) << 2) | 3]) + offset.to_bytes(4, "little"))
+        for _ in range(length):
+            out.append(out[-offset])
+
+    parts, out = [], bytearray()
+    for i in range(24):
+        lit(parts, out, 50000 + 977 * i)
+        if i in (5, 6, 17):
+            cp(parts, out, 64, 300000 + i)
+        if i == 11:
+            cp(parts, out, 40, 70000)
+            cp(parts, out, 64, 131072)
+    put("longrange.snappy", oracle.encode32(len(out)) + b"".join(parts))
+    parts, out = [], bytearray()
+    lit(parts, out, 70000)
+    for i in range(40):
+        lit(parts, out, 30000)
+        cp(parts, out, 64, 65000)
+    put("chained.snappy", oracle.encode32(len(out)) + b"".join(parts))
+    put("mix.snappy", oracle.compress(raw.tobytes()))
+    put("html.snappy", oracle.compress(read_data("html")))
+    files.append(os.path.join(DATA, "alice29.snappy"))
+    p = subprocess.run([exe] + files, env=dict(os.environ, CUTS="1"), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert len(lines) == len(files)
+    for l in lines:
+        assert "[clean cuts ok]" in l and "0 mismatches" in l, l
+
+
 def test_parse_kernel_sources_build_the_true_index(oracle, tmp_path):
     """parse.cuh passes A-E (one thread per 1 KiB of compressed bytes), launched as build_index_segment does, whole
     stream and cut into two segments: whenever the parse accepts a stream its index equals a sequential walk's, clean

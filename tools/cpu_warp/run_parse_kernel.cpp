@@ -7,6 +7,9 @@
 //   flags == 0 and total == claimed  =>  the index equals the true element position at every 64 KiB output boundary
 //   (copy offsets are not the parse's business: the indexed decoder validates every fragment it is given);
 //   a stream the walk finds fragment-clean must come out with flags == 0.
+// CUTS=1: the clean-cut re-tiling (k_cut_low, k_cut_tiles, k_cut_fill; the suffix minimum between them, a multi-warp
+//   kernel, is a plain loop here) against a brute-force computation: tile f must start at the greatest element start
+//   <= f * 65536 that no later copy reaches across.
 #include "../../snappy.jl_b200/csrc/parse.cuh"
 
 #include <string>
@@ -83,11 +86,15 @@ struct SegResult {
 };
 
 // build_index_segment (snappy_b200.cu), kernel for kernel
-static SegResult parse_segment(const u8* in, u64 n, u64 hdr, u64 E, u64 out_base, u32 nfrag, u64* index) {
+static SegResult parse_segment(const u8* in, u64 n, u64 hdr, u64 E, u64 out_base, u32 nfrag, u64* index,
+                               std::vector<u8>* keep_arena = nullptr, std::vector<u64>* keep_off = nullptr,
+                               u64* out_start = nullptr, u64 out_total = 0) {
     const u32 pshift = kParseChunkLog2;
     const u64 pchunk = 1ull << pshift, body = E - hdr;
     const u32 nchunk = (u32)((body + pchunk - 1) / pchunk);
-    std::vector<u8> arena(ParseArrays::bytes(nchunk) + 64, 0);
+    std::vector<u8> own_arena;
+    std::vector<u8>& arena = keep_arena ? *keep_arena : own_arena;
+    arena.assign(ParseArrays::bytes(nchunk) + 64, 0);
     ParseArrays pa;
     pa.carve(arena.data(), nchunk);
     memset(pa.counters, 0, 64);
@@ -108,15 +115,81 @@ static SegResult parse_segment(const u8* in, u64 n, u64 hdr, u64 E, u64 out_base
     launch_independent_threads(pgrid, kParseThreads, k_parse_final, in, n, hdr, nchunk, pa, E, pshift);
     std::vector<u64> out_off(nchunk + 1, 0);  // k_scan_sizes: exclusive scan, total behind the end
     for (u32 k = 0; k < nchunk; k++) out_off[k + 1] = out_off[k] + pa.outb[k];
-    launch_independent_threads(pgrid, kParseThreads, k_build_index, in, n, hdr, nchunk, pa, (const u64*)out_off.data(), index, nfrag,
-                               E, out_base, pshift, (u64*)nullptr, 0u, (u64)0);  // strict form: aligned tiles only
+    if (out_start)  // relaxed form (decode_parsed_locked): tiles may start at a straddling literal
+        launch_independent_threads(pgrid, kParseThreads, k_build_index, in, n, hdr, nchunk, pa, (const u64*)out_off.data(), index, nfrag,
+                                   E, out_base, pshift, out_start, 1u, out_total);
+    else
+        launch_independent_threads(pgrid, kParseThreads, k_build_index, in, n, hdr, nchunk, pa, (const u64*)out_off.data(), index, nfrag,
+                                   E, out_base, pshift, (u64*)nullptr, 0u, (u64)0);  // strict form: aligned tiles only
     u64 host3[4];
     k_parse_report(pa.counters, out_off.data() + nchunk, host3);
+    if (keep_off) *keep_off = out_off;
     return SegResult{host3[0], host3[1], host3[2]};
+}
+
+// the re-tiling of decode_parsed_locked (snappy_b200.cu) against brute force; returns the number of wrong tiles
+static long check_cuts(const u8* in, u64 n, u64 hdr, u32 claimed, u32 nfrag, std::string& note) {
+    std::vector<u8> arena;
+    std::vector<u64> out_off, index(nfrag + 1, ~0ull), ost(nfrag + 1, ~0ull);
+    index[0] = hdr;
+    ost[0] = 0;
+    const SegResult r = parse_segment(in, n, hdr, n, 0, nfrag, index.data(), &arena, &out_off, ost.data(), claimed);
+    if ((r.flags & (PF_ANOMALY | PF_BROKEN)) || r.total != claimed) {
+        note += " [cuts: parse incomplete, skipped]";
+        return 0;
+    }
+    ost[nfrag] = claimed;
+    const u32 pshift = kParseChunkLog2;
+    const u32 nchunk = (u32)(((n - hdr) + (1ull << pshift) - 1) >> pshift);
+    ParseArrays pa;
+    pa.carve(arena.data(), nchunk);
+    std::vector<u64> low(nchunk, 0), sfx(nchunk, ~0ull);
+    const u32 pgrid = (nchunk + kParseThreads - 1) / kParseThreads;
+    launch_independent_threads(pgrid, kParseThreads, k_cut_low, in, n, hdr, nchunk, pa, (const u64*)out_off.data(), n, pshift, low.data());
+    u64 run = ~0ull;  // k_suffix_min
+    for (u32 k = nchunk; k-- > 0;) {
+        sfx[k] = run;
+        run = low[k] < run ? low[k] : run;
+    }
+    if (nfrag > 1)
+        launch_independent_threads((nfrag - 1 + kParseThreads - 1) / kParseThreads, kParseThreads, k_cut_tiles, in, n, hdr, nchunk, pa,
+                                   (const u64*)out_off.data(), (const u64*)sfx.data(), n, pshift, nfrag, index.data(), ost.data());
+    k_cut_fill(nfrag, index.data(), ost.data());
+    // brute force: every element's (output position, stream position, reach), suffix minimum of the reaches
+    struct El { u64 op, ip, reach; };
+    std::vector<El> els;
+    {
+        u64 ip = hdr, op = 0;
+        Element e;
+        while (ip + 1 < n) {
+            const u64 at = ip;
+            if (!walk_step(in, n, ip, e)) break;
+            els.push_back(El{op, at, e.is_copy ? ((u64)e.offset <= op ? op - e.offset : 0) : ~0ull});
+            op += e.len;
+        }
+    }
+    std::vector<u64> R(els.size() + 1, ~0ull);
+    for (size_t i = els.size(); i-- > 0;) R[i] = els[i].reach < R[i + 1] ? els[i].reach : R[i + 1];
+    long bad = 0;
+    size_t j = 0, best = 0;  // best: greatest clean element index with op <= boundary (element 0 is always clean)
+    for (u32 f = 1; f < nfrag; f++) {
+        const u64 B = (u64)f << 16;
+        while (j < els.size() && els[j].op <= B) {
+            if (R[j] >= els[j].op) best = j;
+            j++;
+        }
+        if (ost[f] != els[best].op || index[f] != els[best].ip) {
+            if (bad++ < 3)
+                fprintf(stderr, "tile %u: cut at output %llu (stream %llu), brute force says %llu (%llu)\n", f, (unsigned long long)ost[f],
+                        (unsigned long long)index[f], (unsigned long long)els[best].op, (unsigned long long)els[best].ip);
+        }
+    }
+    return bad;
 }
 
 int main(int argc, char** argv) {
     int failed = 0;
+    const bool cuts = getenv("CUTS") && atoi(getenv("CUTS")) != 0;
     for (int ai = 1; ai < argc; ai++) {
         FILE* fp = fopen(argv[ai], "rb");
         if (!fp) { perror(argv[ai]); return 2; }
@@ -157,6 +230,11 @@ int main(int argc, char** argv) {
                 if (accepted2 && (!t.valid || !t.clean || index2 != t.index)) { ok = false; note += " [two segments: wrong index]"; }
             }
             if (t.valid && t.clean && !accepted2) { ok = false; note += " [two segments: rejected a clean stream]"; }
+        }
+        if (cuts && t.valid) {
+            const long badc = check_cuts(buf.data(), sz, hdr, claimed, nfrag, note);
+            if (badc) { ok = false; note += " [clean cuts: " + std::to_string(badc) + " wrong tiles]"; }
+            else note += " [clean cuts ok]";
         }
         printf("%s: %u fragments, stream %s%s/%s, parse %s (flags %llu, total %llu of %u), two segments %s: %s%s\n", argv[ai], nfrag,
                t.valid ? "valid" : "INVALID", t.offsets_ok ? "" : " (bad copy offset)", t.clean ? "clean" : "not clean", accepted ? "accepted" : "declined",
