@@ -53,6 +53,12 @@ static unsigned long g_emu_rounds = 0, g_emu_second = 0;  // tools/cpu_warp: rou
 #ifndef SB200_M_BRANCHFREE
 #define SB200_M_BRANCHFREE 1
 #endif
+// match length of a lane: the first differing word decides, one find-first-set instead of four (12.59 -> 12.40 ms
+// per GiB of the mix, 13.59 -> 13.33 ms on source-like text, profiles/r02y_sweep_micro.txt).  Tried with it and
+// dropped: no gather for the lanes whose hash equals a lower lane's (never trusted) -- slower, 14.6 ms on text.
+#ifndef SB200_M_ONE_FFS
+#define SB200_M_ONE_FFS 1
+#endif
 
 // kSlowCont (option `slowcont`, experimental, off): a copy of >= 16 bytes is extended inside the hop loop and the
 // chain goes on in the same window when it lands there, instead of ending the round (tools/emulate_window.c
@@ -250,7 +256,12 @@ struct Win : Chain<kSmemTable, kLib> {
         {
             const u32 x0 = C0 ^ B0, x1 = __funnelshift_r(c1, c2, tsh) ^ B1,
                       x2 = __funnelshift_r(c2, c3, tsh) ^ B2, x3 = __funnelshift_r(c3, c4, tsh) ^ B3;
-#if SB200_M_BRANCHFREE
+#if SB200_M_ONE_FFS
+            // the first word that differs decides: one find-first-set instead of four
+            const u32 w = x0 ? x0 : (x1 ? x1 : (x2 ? x2 : x3));
+            const u32 base = x0 ? 0u : (x1 ? 4u : (x2 ? 8u : 12u));
+            m = w ? base + (((u32)__ffs((int)w) - 1u) >> 3) : 16u;
+#elif SB200_M_BRANCHFREE
             // equal bytes per word (0..4), then the length of the run of full words: no divergent branches
             const u32 m0 = x0 ? ((u32)__ffs((int)x0) - 1u) >> 3 : 4u, m1 = x1 ? ((u32)__ffs((int)x1) - 1u) >> 3 : 4u,
                       m2 = x2 ? ((u32)__ffs((int)x2) - 1u) >> 3 : 4u, m3 = x3 ? ((u32)__ffs((int)x3) - 1u) >> 3 : 4u;
