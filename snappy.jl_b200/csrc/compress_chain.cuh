@@ -84,6 +84,7 @@ struct Chain {
     u32 n, shift, lane, op, nrec, spec;  // spec: end positions pre-probed per copy (<= 32)
     int lim;
     u32 r_lit, r_cpy;  // lane k parks record k: (lit_from | ip << 16), (cand | M << 16)
+    u64 pol;           // L2 cache policy of the global-table accesses (evict_last), make_policy()
     bool dyn_smem;     // kSmemTable == 2 only
     __device__ __forceinline__ bool in_smem() const { return kSmemTable == 2 ? dyn_smem : kSmemTable == 1; }
 
@@ -91,6 +92,7 @@ struct Chain {
         return kLib ? (((w * kHashMul) >> shift) & hmask) : ((w * kHashMul) >> shift);
     }
 #ifdef SB200_CPU_EMU
+    __device__ __forceinline__ void make_policy() { pol = 0; }
     __device__ __forceinline__ u32 tget(u32 h) const {
         return in_smem() ? *reinterpret_cast<const u16*>(smem + Ts + 2u * h) : T[h];
     }
@@ -107,13 +109,18 @@ struct Chain {
         }
         // global tables: keep their lines in L2 ahead of everything that streams through it (evict_last):
         // -4 % kernel time, they are the randomly re-read state
+        // (the policy is made once per fragment, make_policy(): as part of every access `createpolicy` cost six
+        // uniform-datapath instructions, three times per round)
         u16 v;
-        asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; ld.global.cg.L2::cache_hint.u16 %0, [%1], pol; }" : "=h"(v) : "l"(T + h) : "memory");
+        asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(T + h), "l"(pol) : "memory");
         return v;
     }
     __device__ __forceinline__ void tput(u32 h, u32 pos) const {
         if (in_smem()) asm volatile("st.shared.u16 [%0], %1;" ::"r"(Ts + 2u * h), "h"((u16)pos) : "memory");
-        else asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; st.global.cg.L2::cache_hint.u16 [%0], %1, pol; }" ::"l"(T + h), "h"((u16)pos) : "memory");
+        else asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(T + h), "h"((u16)pos), "l"(pol) : "memory");
+    }
+    __device__ __forceinline__ void make_policy() {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     }
 #endif
 
@@ -451,6 +458,7 @@ k_compress_chain(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shif
         ch.shift = fshift;
         ch.lane = lane;
         ch.spec = spec_lanes;
+        ch.make_policy();
         ch.run();
         if (lane == 0) frag_sizes[frag] = ch.op;
         __syncwarp();

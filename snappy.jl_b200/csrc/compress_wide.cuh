@@ -135,6 +135,7 @@ k_compress_wide(const u8* __restrict__ g_in, u64 shard_len, u32 nfrag, u32 shift
         ch.shift = fshift;
         ch.lane = lane;
         ch.spec = 0;
+        ch.make_policy();
         ch.Rs = ring;
         ch.rmask = ring_bytes - 1u;
         ch.lo = ch.hi = 0;

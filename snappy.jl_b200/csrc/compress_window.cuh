@@ -30,7 +30,8 @@
 // bytes first and the other 12 on a hit saves wavefronts but costs a second round trip: +6..9 %).
 // tools/emulate_window.c is the CPU model of this file; it is checked against the oracle on every fixture.
 // (The two compile-time switches below are measured and decided; the dead arms stay because removing them
-// changed ptxas' schedule of the round for the worse: 26.1 vs 22.8 ms for the shared-table kernel.)
+// changed ptxas' schedule of the round for the worse: 26.1 vs 22.8 ms for the shared-table kernel in round 1, and
+// again in round 2: 12.84 vs 12.19 ms for the merged kernel, profiles/r02zb_sweep_policy.txt.)
 #pragma once
 #include <type_traits>
 #include "compress_chain.cuh"
