@@ -591,6 +591,7 @@ __device__ __forceinline__ void window_warp_loop(const WindowArgs& A, u16* T, u3
         ch.shift = fshift;
         ch.lane = lane;
         ch.spec = 0;
+        ch.make_policy();
         ch.Rs = ring;
         ch.rmask = ring_bytes - 1u;
         ch.lo = ch.hi = 0;
@@ -742,6 +743,7 @@ k_compress_pages_window(const u8* __restrict__ g_in, const u64* __restrict__ in_
         ch.shift = fshift;
         ch.lane = lane;
         ch.spec = 0;
+        ch.make_policy();
         ch.Rs = smem_u32(R);
         ch.rmask = ring_bytes - 1u;
         ch.lo = 0;
