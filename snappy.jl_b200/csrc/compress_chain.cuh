@@ -72,6 +72,9 @@ __global__ void k_init_probe_offsets() {
 
 // kSmemTable: 1 = the table lives in shared memory, 0 = in global memory (L2), 2 = either, decided per warp at run time
 // (dyn_smem): ONE copy of the round's code serves both kinds of warp of the merged kernel (instruction cache).
+#ifndef SB200_FLUSH_NOINLINE
+#define SB200_FLUSH_NOINLINE 0
+#endif
 template <int kSmemTable, bool kLib = false>
 struct Chain {
     static constexpr u32 kLitShort = kLib ? 61u : 60u;   // literals below this take the one-byte header (:271)
@@ -154,7 +157,11 @@ struct Chain {
         return p + 3;
     }
 
+#if SB200_FLUSH_NOINLINE && !defined(SB200_CPU_EMU)
+    __device__ __noinline__ void flush() {
+#else
     __device__ __forceinline__ void flush() {
+#endif
         {   // pull the next few KiB of the fragment into L2 ahead of the ip-side loads (32 x 128 B)
             const u32 ahead = (r_lit >> 16) + kStreamAhead + lane * 128u;  // from this lane's ip
 #ifndef SB200_CPU_EMU
