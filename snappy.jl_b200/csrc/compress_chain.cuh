@@ -75,6 +75,9 @@ __global__ void k_init_probe_offsets() {
 #ifndef SB200_FLUSH_NOINLINE
 #define SB200_FLUSH_NOINLINE 0
 #endif
+#ifndef SB200_PIN_OUT
+#define SB200_PIN_OUT 0
+#endif
 template <int kSmemTable, bool kLib = false>
 struct Chain {
     static constexpr u32 kLitShort = kLib ? 61u : 60u;   // literals below this take the one-byte header (:271)
@@ -182,6 +185,13 @@ struct Chain {
         }
         const u32 pos = op + incl - sz;
         op += __shfl_sync(kFullMask, incl, 31);
+#if SB200_PIN_OUT && !defined(SB200_CPU_EMU)
+        // build switch, off: keep the slot's base address in a register pair; ptxas otherwise rebuilds it (constant-bank
+        // load, 64-bit multiply-add with the fragment number) in front of every group of byte stores below.  328 fewer
+        // SASS instructions, 92 registers, and no faster: 12.28 vs 12.21 ms (profiles/r02zi_sweep_pin_out.txt)
+        u8* out = this->out;
+        asm volatile("" : "+l"(out));
+#endif
 #ifdef SB200_EXPERIMENTS
         if (g_dbg_skip_emit) {  // measurement only (option dbg_skip_emit): sizes stay right, bytes are not written
             nrec = 0;
